@@ -1,0 +1,1027 @@
+// C ABI of libfeast_cuda.so: context, operator upload, and the three per-iteration phases
+// (project / recover+residual / contour apply) of the FEAST outer loop, plus the
+// fine-grained factorizer / left_divider plugin pair.  See include/feast_cuda.h for the
+// reference statements each entry replaces.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+
+#include "host_small.h"
+#include "kernels.cuh"
+#include "nccl_dl.h"
+
+std::string g_last_error;
+
+int feast_fail(feast_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define ARG_CHECK(ctx, cond, k, msg) \
+    do { if (!(cond)) return feast_fail(ctx, -(k), "argument %d invalid: %s", (k), msg); } while (0)
+
+// ------------------------------------------------------------------------------- helpers
+namespace {
+
+template <typename T>
+int dev_alloc(feast_ctx* ctx, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, sizeof(T) * (count ? count : 1));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return feast_fail(ctx, e == cudaErrorMemoryAllocation ? FEAST_ERR_OOM : FEAST_ERR_CUDA,
+                          "cudaMalloc of %zu bytes failed: %s", sizeof(T) * count, cudaGetErrorString(e));
+    }
+    *p = (T*)q;
+    return 0;
+}
+template <typename T>
+void dev_free(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+int bind_device(feast_ctx* ctx) {
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return 0;
+}
+
+void free_operator(Operator& op) {
+    dev_free(op.dense);
+    dev_free(op.uvals_r);
+    dev_free(op.uvals_c);
+    op = Operator();
+}
+
+void free_problem_derived(feast_ctx* ctx) {
+    dev_free(ctx->u_rowptr);
+    dev_free(ctx->u_col);
+    dev_free(ctx->zvals);
+    dev_free(ctx->zdense);
+    dev_free(ctx->zpiv);
+    for (auto& f : ctx->stored) { dev_free(f.lu); dev_free(f.ipiv); dev_free(f.perm); }
+    ctx->stored.clear();
+    for (int i = 0; i < FEAST_MAX_SLOTS; ++i) { dev_free(ctx->ops[i].uvals_r); dev_free(ctx->ops[i].uvals_c); }
+    ctx->problem_ready = false;
+}
+
+void free_blocks(feast_ctx* ctx) {
+    BlockVec* all[] = {&ctx->Q, &ctx->X, &ctx->R, &ctx->Q1, &ctx->W1, &ctx->W2, &ctx->kx, &ctx->kr,
+                       &ctx->kp, &ctx->kq, &ctx->ks, &ctx->kt, &ctx->kv, &ctx->krh};
+    for (auto* b : all) dev_free(b->p);
+    dev_free(ctx->stage);
+    dev_free(ctx->small_d);
+    dev_free(ctx->red_d);
+    ctx->red_bytes = 0;
+    ctx->m0 = 0;
+}
+
+int ensure_block(feast_ctx* ctx, BlockVec& b) {
+    if (b.p) return 0;
+    return dev_alloc(ctx, &b.p, (size_t)ctx->n * ctx->m0);
+}
+
+int ensure_pinned(feast_ctx* ctx, size_t bytes) {
+    if (ctx->pinned_bytes >= bytes) return 0;
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    CUDA_TRY(ctx, cudaMallocHost(&ctx->pinned, bytes));
+    ctx->pinned_bytes = bytes;
+    return 0;
+}
+
+struct PhaseTimer {  // CUDA-event timing of a phase on the library stream
+    feast_ctx* ctx; int idx; bool on;
+    PhaseTimer(feast_ctx* c, int i) : ctx(c), idx(i), on(true) { cudaEventRecord(ctx->ev0, ctx->stream); }
+    double stop() {
+        if (!on) return 0.0;
+        on = false;
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaEventSynchronize(ctx->ev1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (idx >= 0) ctx->phase_ms[idx] += ms;
+        return ms;
+    }
+};
+
+// --------------------------------------------------------------------- operator application
+// W = op(slot) * V   (row-major n x m0 blocks)
+int apply_slot(feast_ctx* ctx, int slot, const c128* V, c128* W) {
+    const Operator& op = ctx->ops[slot];
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    if (op.kind == OP_IDENTITY) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(W, V, sizeof(c128) * n * m, cudaMemcpyDeviceToDevice, ctx->stream));
+        return 0;
+    }
+    if (op.kind == OP_DENSE)
+        return launch_zgemm(ctx, (int)n, m, n, hc128(1, 0), op.dense, 1, n, false, V, m, 1, hc128(0, 0), W, m, 1);
+    if (op.kind == OP_CSR)
+        return launch_spmm(ctx, n, m, ctx->u_rowptr, ctx->u_col, op.uvals_r, op.uvals_c, V, m, W, m, nullptr);
+    return feast_fail(ctx, FEAST_ERR_STATE, "operator slot %d is not set", slot);
+}
+
+// CSC (possibly 1-based, int64) -> host CSR with sorted columns; also detects S == S^T
+int csc_to_host_csr(feast_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const void* nzval,
+                    int is_complex, int base, HostCSR& out) {
+    const int64_t nnz = colptr[n] - base;
+    if (nnz < 0) return feast_fail(ctx, -4, "argument 4 invalid: colptr not monotone");
+    out.n = n; out.nnz = nnz; out.is_complex = is_complex != 0;
+    out.rowptr.assign(n + 1, 0);
+    out.col.resize(nnz);
+    out.val.resize(nnz);
+    for (int64_t e = 0; e < nnz; ++e) {
+        const int64_t r = rowval[e] - base;
+        if (r < 0 || r >= n) return feast_fail(ctx, -5, "argument 5 invalid: row index out of range");
+        out.rowptr[r + 1]++;
+    }
+    for (int64_t i = 0; i < n; ++i) out.rowptr[i + 1] += out.rowptr[i];
+    std::vector<int64_t> cursor(out.rowptr.begin(), out.rowptr.end() - 1);
+    const double* rv = (const double*)nzval;
+    for (int64_t c = 0; c < n; ++c) {
+        for (int64_t e = colptr[c] - base; e < colptr[c + 1] - base; ++e) {
+            const int64_t r = rowval[e] - base;
+            const int64_t d = cursor[r]++;
+            out.col[d] = (int)c;
+            out.val[d] = is_complex ? hc128(rv[2 * e], rv[2 * e + 1]) : hc128(rv[e], 0.0);
+        }
+    }
+    // columns visited in increasing order -> each CSR row is already sorted by column.
+    // symmetry: compare CSR(S) with CSC(S) == CSR(S^T) when the CSC rows are sorted too
+    bool sym = true;
+    for (int64_t c = 0; c < n && sym; ++c) {
+        const int64_t a0 = colptr[c] - base, a1 = colptr[c + 1] - base;
+        if (a1 - a0 != out.rowptr[c + 1] - out.rowptr[c]) { sym = false; break; }
+        for (int64_t e = a0; e < a1; ++e) {
+            const int64_t d = out.rowptr[c] + (e - a0);
+            const hc128 v = is_complex ? hc128(rv[2 * e], rv[2 * e + 1]) : hc128(rv[e], 0.0);
+            if (rowval[e] - base != out.col[d] || v != out.val[d]) { sym = false; break; }
+        }
+    }
+    out.symmetric = sym;
+    return 0;
+}
+
+// Build the union CSR pattern over all sparse / identity slots and the per-slot value arrays.
+int build_union(feast_ctx* ctx) {
+    const int64_t n = ctx->n;
+    std::vector<int64_t> rowptr(n + 1, 0);
+    std::vector<int> col;
+    // pass 1: merged pattern row by row
+    std::vector<const HostCSR*> hs;
+    bool any_identity = false;
+    for (int s = 0; s < ctx->nslots; ++s) {
+        if (ctx->ops[s].kind == OP_CSR) hs.push_back(&ctx->ops[s].host);
+        if (ctx->ops[s].kind == OP_IDENTITY) any_identity = true;
+    }
+    size_t reserve = 0;
+    for (auto* h : hs) reserve = std::max(reserve, (size_t)h->nnz);
+    col.reserve(reserve + (any_identity ? n : 0));
+    std::vector<int64_t> pos(hs.size());
+    for (int64_t i = 0; i < n; ++i) {
+        for (size_t k = 0; k < hs.size(); ++k) pos[k] = hs[k]->rowptr[i];
+        bool diag_pending = any_identity;
+        while (true) {
+            int best = INT32_MAX;
+            for (size_t k = 0; k < hs.size(); ++k)
+                if (pos[k] < hs[k]->rowptr[i + 1]) best = std::min(best, hs[k]->col[pos[k]]);
+            if (diag_pending && (int)i < best) best = (int)i;
+            if (best == INT32_MAX) break;
+            if (best == (int)i) diag_pending = false;
+            col.push_back(best);
+            for (size_t k = 0; k < hs.size(); ++k)
+                if (pos[k] < hs[k]->rowptr[i + 1] && hs[k]->col[pos[k]] == best) pos[k]++;
+        }
+        rowptr[i + 1] = (int64_t)col.size();
+    }
+    const int64_t unnz = (int64_t)col.size();
+    if (unnz > INT32_MAX) return feast_fail(ctx, FEAST_ERR_STATE, "union pattern exceeds 2^31 nonzeros");
+    ctx->unnz = unnz;
+    std::vector<int> rp32(n + 1);
+    for (int64_t i = 0; i <= n; ++i) rp32[i] = (int)rowptr[i];
+    FEAST_TRY(dev_alloc(ctx, &ctx->u_rowptr, n + 1));
+    FEAST_TRY(dev_alloc(ctx, &ctx->u_col, unnz));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->u_rowptr, rp32.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->u_col, col.data(), sizeof(int) * unnz, cudaMemcpyHostToDevice));
+    // pass 2: per-slot values on the union pattern
+    bool all_sym = true;
+    for (int s = 0; s < ctx->nslots; ++s) {
+        Operator& op = ctx->ops[s];
+        std::vector<double> rv;
+        std::vector<hc128> cv;
+        const bool cplx = (op.kind == OP_CSR) && op.host.is_complex;
+        if (cplx) cv.assign(unnz, hc128(0, 0)); else rv.assign(unnz, 0.0);
+        if (op.kind == OP_IDENTITY) {
+            for (int64_t i = 0; i < n; ++i) {
+                auto it = std::lower_bound(col.begin() + rowptr[i], col.begin() + rowptr[i + 1], (int)i);
+                rv[it - col.begin()] = 1.0;
+            }
+            op.symmetric = true;
+        } else if (op.kind == OP_CSR) {
+            const HostCSR& h = op.host;
+            for (int64_t i = 0; i < n; ++i) {
+                int64_t u = rowptr[i];
+                for (int64_t e = h.rowptr[i]; e < h.rowptr[i + 1]; ++e) {
+                    while (col[u] != h.col[e]) ++u;
+                    if (cplx) cv[u] = h.val[e]; else rv[u] = h.val[e].real();
+                }
+            }
+            op.symmetric = h.symmetric;
+        } else {
+            return feast_fail(ctx, FEAST_ERR_STATE, "slot %d is not set (sparse problem)", s);
+        }
+        all_sym = all_sym && op.symmetric;
+        op.is_complex = cplx;
+        if (cplx) {
+            FEAST_TRY(dev_alloc(ctx, &op.uvals_c, unnz));
+            CUDA_TRY(ctx, cudaMemcpy(op.uvals_c, cv.data(), sizeof(c128) * unnz, cudaMemcpyHostToDevice));
+        } else {
+            FEAST_TRY(dev_alloc(ctx, &op.uvals_r, unnz));
+            CUDA_TRY(ctx, cudaMemcpy(op.uvals_r, rv.data(), sizeof(double) * unnz, cudaMemcpyHostToDevice));
+        }
+        // host copies are kept so that feast_set_problem can be called again (e.g. switching the
+        // problem kind); an identity slot keeps its kind and additionally lives on the union pattern
+    }
+    ctx->all_symmetric = all_sym;
+    FEAST_TRY(dev_alloc(ctx, &ctx->zvals, unnz));
+    return 0;
+}
+
+int effective_solver(const feast_ctx* ctx) {
+    if (ctx->solver != FEAST_SOLVER_AUTO) return ctx->solver;
+    if (ctx->storage_dense) return FEAST_SOLVER_DENSE_LU;
+    return ctx->n <= ctx->dense_threshold ? FEAST_SOLVER_DENSE_LU : FEAST_SOLVER_KRYLOV;
+}
+int effective_krylov(const feast_ctx* ctx) {
+    if (ctx->krylov != FEAST_KRYLOV_AUTO) return ctx->krylov;
+    return ctx->all_symmetric ? FEAST_KRYLOV_COCG : FEAST_KRYLOV_BICGSTAB;
+}
+
+// Z = sum_i coef[i] * slot_i, assembled either dense (col-major n x n) or on the union pattern
+int assemble_dense_Z(feast_ctx* ctx, const hc128* coef, c128* Z) {
+    const int64_t n = ctx->n;
+    if (ctx->storage_dense) {
+        const c128* D[FEAST_MAX_SLOTS];
+        int kinds[FEAST_MAX_SLOTS];
+        for (int s = 0; s < ctx->nslots; ++s) { D[s] = ctx->ops[s].dense; kinds[s] = ctx->ops[s].kind; }
+        return launch_assemble_dense(ctx, n, ctx->nslots, D, kinds, coef, Z);
+    }
+    const double* rv[FEAST_MAX_SLOTS];
+    const c128* cv[FEAST_MAX_SLOTS];
+    for (int s = 0; s < ctx->nslots; ++s) { rv[s] = ctx->ops[s].uvals_r; cv[s] = ctx->ops[s].uvals_c; }
+    FEAST_TRY(launch_assemble_union(ctx, ctx->unnz, ctx->nslots, rv, cv, coef, ctx->zvals));
+    return launch_scatter_dense(ctx, n, ctx->u_rowptr, ctx->u_col, ctx->zvals, Z);
+}
+int assemble_sparse_Z(feast_ctx* ctx, const hc128* coef, c128* zvals) {
+    const double* rv[FEAST_MAX_SLOTS];
+    const c128* cv[FEAST_MAX_SLOTS];
+    for (int s = 0; s < ctx->nslots; ++s) { rv[s] = ctx->ops[s].uvals_r; cv[s] = ctx->ops[s].uvals_c; }
+    return launch_assemble_union(ctx, ctx->unnz, ctx->nslots, rv, cv, coef, zvals);
+}
+
+void node_coefs(const feast_ctx* ctx, hc128 z, hc128* coef) {
+    if (ctx->problem == FEAST_PROBLEM_POLYNOMIAL) {
+        hc128 p(1, 0);
+        for (int s = 0; s < ctx->nslots; ++s) { coef[s] = p; p *= z; }
+    } else {  // A - z B   (src/feast.jl:64,141)
+        coef[0] = hc128(1, 0);
+        coef[1] = -z;
+    }
+}
+
+int ensure_krylov_work(feast_ctx* ctx, int method) {
+    FEAST_TRY(ensure_block(ctx, ctx->kr));
+    FEAST_TRY(ensure_block(ctx, ctx->kp));
+    FEAST_TRY(ensure_block(ctx, ctx->kq));
+    if (method == FEAST_KRYLOV_BICGSTAB) {
+        FEAST_TRY(ensure_block(ctx, ctx->krh));
+        FEAST_TRY(ensure_block(ctx, ctx->kv));
+        FEAST_TRY(ensure_block(ctx, ctx->ks));
+        FEAST_TRY(ensure_block(ctx, ctx->kt));
+    }
+    return 0;
+}
+
+int factor_dense(feast_ctx* ctx, const hc128* coef, DenseLU& f, int* info) {
+    const int64_t n = ctx->n;
+    f.n = n;
+    if (!f.lu) FEAST_TRY(dev_alloc(ctx, &f.lu, (size_t)n * n));
+    if (!f.ipiv) FEAST_TRY(dev_alloc(ctx, &f.ipiv, n));
+    if (!f.perm) FEAST_TRY(dev_alloc(ctx, &f.perm, n));
+    FEAST_TRY(assemble_dense_Z(ctx, coef, f.lu));
+    FEAST_TRY(dense_getrf(ctx, n, f.lu, f.ipiv, info));
+    FEAST_TRY(dense_build_perm(ctx, n, f.ipiv, f.perm));
+    return 0;
+}
+
+// iterated Cholesky-QR with column scaling and clamped pivots; V <- orth(V), V_in = V_out * Rtot
+int orthonormalize(feast_ctx* ctx, BlockVec& V, std::vector<hc128>* Rtot_out) {
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    FEAST_TRY(ensure_block(ctx, ctx->W1));
+    FEAST_TRY(ensure_pinned(ctx, sizeof(hc128) * (size_t)m * m + 256));
+    std::vector<hc128> G((size_t)m * m), R, Ri, Rtot, tmp;
+    if (Rtot_out) {
+        Rtot.assign((size_t)m * m, hc128(0, 0));
+        for (int j = 0; j < m; ++j) Rtot[(size_t)j * m + j] = 1.0;
+    }
+    c128* G_d = ctx->small_d;
+    c128* M_d = ctx->small_d + (size_t)m * m;
+    const int maxpass = 8;
+    const double tau = 64.0 * m * 2.2e-16;
+    for (int pass = 0; pass < maxpass; ++pass) {
+        FEAST_TRY(launch_gram(ctx, n, m, V.p, V.p, G_d));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, G_d, sizeof(c128) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(G.data(), ctx->pinned, sizeof(hc128) * m * m);
+        std::vector<double> d(m);
+        for (int j = 0; j < m; ++j) {
+            const double g = G[(size_t)j * m + j].real();
+            d[j] = (g > 0.0 && std::isfinite(g)) ? std::sqrt(g) : 1.0;
+        }
+        double dev = 0.0;
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < m; ++i) {
+                hc128 g = G[(size_t)j * m + i] / (d[i] * d[j]);
+                G[(size_t)j * m + i] = g;
+                dev = std::max(dev, std::abs(g - (i == j ? hc128(1, 0) : hc128(0, 0))));
+            }
+        bool scaled_only = true;
+        for (int j = 0; j < m; ++j) if (std::fabs(d[j] - 1.0) > 4e-16) scaled_only = false;
+        if (dev <= 8e-16 * std::sqrt((double)m) + 4e-16 && scaled_only) break;  // orthonormal to rounding
+        chol_upper_clamped(m, G, R, tau);
+        triu_inverse(m, R, Ri);
+        // V_new = V * D^-1 * R^-1
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < m; ++i) Ri[(size_t)j * m + i] /= d[i];
+        CUDA_TRY(ctx, cudaMemcpyAsync(M_d, Ri.data(), sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
+        FEAST_TRY(launch_update(ctx, n, m, V.p, M_d, ctx->W1.p));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // Ri is a host temporary
+        std::swap(V.p, ctx->W1.p);
+        if (Rtot_out) {  // Rtot <- R * D * Rtot
+            for (int j = 0; j < m; ++j)
+                for (int i = 0; i < m; ++i) R[(size_t)j * m + i] *= d[j];
+            matmul_small(m, R, Rtot, tmp);
+            Rtot.swap(tmp);
+        }
+    }
+    if (Rtot_out) Rtot_out->swap(Rtot);
+    return 0;
+}
+
+int check_ready(feast_ctx* ctx, bool need_subspace) {
+    if (!ctx) return feast_fail(nullptr, -1, "argument 1 invalid: null context");
+    if (!ctx->problem_ready) return feast_fail(ctx, FEAST_ERR_STATE, "feast_set_problem has not been called");
+    if (need_subspace && ctx->m0 == 0) return feast_fail(ctx, FEAST_ERR_STATE, "feast_set_subspace has not been called");
+    return bind_device(ctx);
+}
+
+int download_block(feast_ctx* ctx, const BlockVec& b, feast_c128* H, int64_t ld) {
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    if (!b.p) return feast_fail(ctx, FEAST_ERR_STATE, "requested block has not been computed yet");
+    FEAST_TRY(launch_rowmajor_to_colmajor(ctx, n, m, b.p, ctx->stage, n));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(H, sizeof(c128) * ld, ctx->stage, sizeof(c128) * n, sizeof(c128) * n, m,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================== ABI
+extern "C" {
+
+int feast_version(void) { return 100; }
+
+int feast_device_count(int* count) {
+    if (!count) return -1;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return feast_fail(nullptr, FEAST_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+int feast_ctx_create(feast_ctx** out, int device) {
+    if (!out) return feast_fail(nullptr, -1, "argument 1 invalid: null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return feast_fail(nullptr, FEAST_ERR_CUDA,
+                          "no CUDA device available (%s); libfeast_cuda has no CPU fallback",
+                          e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= count) return feast_fail(nullptr, -2, "argument 2 invalid: device %d of %d", device, count);
+    feast_ctx* ctx = new feast_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        int rc = feast_fail(nullptr, FEAST_ERR_CUDA, "context creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete ctx;
+        return rc;
+    }
+    if (ensure_pinned(ctx, 1 << 20)) { delete ctx; return FEAST_ERR_CUDA; }
+    *out = ctx;
+    return 0;
+}
+
+int feast_ctx_destroy(feast_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->nccl_comm) { const NcclApi* api = nccl_api(); if (api) api->CommDestroy(ctx->nccl_comm); }
+    free_problem_derived(ctx);
+    for (int i = 0; i < FEAST_MAX_SLOTS; ++i) free_operator(ctx->ops[i]);
+    free_blocks(ctx);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+const char* feast_last_error(const feast_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+// ------------------------------------------------------------------------- operators
+int feast_set_dense(feast_ctx* ctx, int slot, int64_t n, const void* a, int64_t lda, int is_complex) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, slot >= 0 && slot < FEAST_MAX_SLOTS, 2, "slot out of range");
+    ARG_CHECK(ctx, n > 0, 3, "n must be positive");
+    ARG_CHECK(ctx, a != nullptr, 4, "null matrix");
+    ARG_CHECK(ctx, lda >= n, 5, "lda < n");
+    FEAST_TRY(bind_device(ctx));
+    free_problem_derived(ctx);
+    free_operator(ctx->ops[slot]);
+    Operator& op = ctx->ops[slot];
+    FEAST_TRY(dev_alloc(ctx, &op.dense, (size_t)n * n));
+    if (is_complex) {
+        CUDA_TRY(ctx, cudaMemcpy2D(op.dense, sizeof(c128) * n, a, sizeof(c128) * lda, sizeof(c128) * n, n, cudaMemcpyHostToDevice));
+    } else {
+        double* tmp = nullptr;
+        FEAST_TRY(dev_alloc(ctx, &tmp, (size_t)n * n));
+        cudaError_t e = cudaMemcpy2D(tmp, sizeof(double) * n, a, sizeof(double) * lda, sizeof(double) * n, n, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            int rc = launch_real_to_complex(ctx, n * n, tmp, op.dense);
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(tmp);
+            if (rc) return rc;
+        } else {
+            cudaFree(tmp);
+            return feast_fail(ctx, FEAST_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+        }
+    }
+    op.kind = OP_DENSE; op.n = n; op.is_complex = true;
+    return 0;
+}
+
+int feast_set_csc(feast_ctx* ctx, int slot, int64_t n, const int64_t* colptr, const int64_t* rowval, const void* nzval,
+                  int is_complex, int index_base) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, slot >= 0 && slot < FEAST_MAX_SLOTS, 2, "slot out of range");
+    ARG_CHECK(ctx, n > 0 && n < INT32_MAX, 3, "n out of range");
+    ARG_CHECK(ctx, colptr != nullptr, 4, "null colptr");
+    ARG_CHECK(ctx, rowval != nullptr || colptr[n] == index_base, 5, "null rowval");
+    ARG_CHECK(ctx, nzval != nullptr || colptr[n] == index_base, 6, "null nzval");
+    ARG_CHECK(ctx, index_base == 0 || index_base == 1, 8, "index_base must be 0 or 1");
+    FEAST_TRY(bind_device(ctx));
+    free_problem_derived(ctx);
+    free_operator(ctx->ops[slot]);
+    Operator& op = ctx->ops[slot];
+    FEAST_TRY(csc_to_host_csr(ctx, n, colptr, rowval, nzval, is_complex, index_base, op.host));
+    op.kind = OP_CSR; op.n = n; op.is_complex = is_complex != 0;
+    return 0;
+}
+
+int feast_set_identity(feast_ctx* ctx, int slot, int64_t n) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, slot >= 0 && slot < FEAST_MAX_SLOTS, 2, "slot out of range");
+    ARG_CHECK(ctx, n > 0, 3, "n must be positive");
+    FEAST_TRY(bind_device(ctx));
+    free_problem_derived(ctx);
+    free_operator(ctx->ops[slot]);
+    ctx->ops[slot].kind = OP_IDENTITY;
+    ctx->ops[slot].n = n;
+    ctx->ops[slot].symmetric = true;
+    return 0;
+}
+
+int feast_set_problem(feast_ctx* ctx, int kind, int nslots) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, kind >= FEAST_PROBLEM_STANDARD && kind <= FEAST_PROBLEM_POLYNOMIAL, 2, "unknown problem kind");
+    ARG_CHECK(ctx, nslots >= 1 && nslots <= FEAST_MAX_SLOTS, 3, "nslots out of range");
+    if (kind == FEAST_PROBLEM_STANDARD) ARG_CHECK(ctx, nslots == 1, 3, "standard problem has one operator");
+    if (kind == FEAST_PROBLEM_GENERALIZED) ARG_CHECK(ctx, nslots == 2, 3, "generalized problem has two operators");
+    if (kind == FEAST_PROBLEM_POLYNOMIAL) ARG_CHECK(ctx, nslots >= 2, 3, "polynomial problem needs degree >= 1");
+    FEAST_TRY(bind_device(ctx));
+    free_problem_derived(ctx);
+    if (ctx->ops[0].kind == OP_NONE) return feast_fail(ctx, FEAST_ERR_STATE, "slot 0 (A) is not set");
+    const int64_t n = ctx->ops[0].n;
+    if (kind == FEAST_PROBLEM_STANDARD) {  // B = I implicitly (src/feast.jl:64 `A - I*z`)
+        free_operator(ctx->ops[1]);
+        ctx->ops[1].kind = OP_IDENTITY; ctx->ops[1].n = n; ctx->ops[1].symmetric = true;
+        nslots = 2;
+    }
+    bool any_dense = false, any_sparse = false;
+    for (int s = 0; s < nslots; ++s) {
+        const Operator& op = ctx->ops[s];
+        if (op.kind == OP_NONE) return feast_fail(ctx, FEAST_ERR_STATE, "slot %d is not set", s);
+        if (op.n != n) return feast_fail(ctx, FEAST_ERR_STATE, "slot %d has dimension %lld, expected %lld", s, (long long)op.n, (long long)n);
+        any_dense |= op.kind == OP_DENSE;
+        any_sparse |= op.kind == OP_CSR;
+    }
+    if (any_dense && any_sparse)
+        return feast_fail(ctx, FEAST_ERR_STATE, "mixing dense and sparse operators is not supported: densify on the caller side");
+    if (!any_dense && !any_sparse) return feast_fail(ctx, FEAST_ERR_STATE, "all operators are identities");
+    ctx->problem = kind; ctx->nslots = nslots; ctx->n = n; ctx->storage_dense = any_dense;
+    if (ctx->m0 != 0) free_blocks(ctx);  // a new problem invalidates the subspace blocks
+    if (!any_dense) FEAST_TRY(build_union(ctx));
+    ctx->problem_ready = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------- contour / solver / comm
+int feast_set_contour(feast_ctx* ctx, int nnodes, const feast_c128* z, const feast_c128* w) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, nnodes >= 1, 2, "need at least one node");
+    ARG_CHECK(ctx, z != nullptr, 3, "null nodes");
+    ARG_CHECK(ctx, w != nullptr, 4, "null weights");
+    ctx->znodes.resize(nnodes);
+    ctx->zweights.resize(nnodes);
+    for (int k = 0; k < nnodes; ++k) { ctx->znodes[k] = hc128(z[k].re, z[k].im); ctx->zweights[k] = hc128(w[k].re, w[k].im); }
+    // default owners: round-robin pairs node k with node k + nnodes/2 on the same rank when possible
+    ctx->owner.assign(nnodes, 0);
+    for (int k = 0; k < nnodes; ++k) ctx->owner[k] = k % ctx->nranks;
+    for (auto& f : ctx->stored) { dev_free(f.lu); dev_free(f.ipiv); dev_free(f.perm); }
+    ctx->stored.clear();
+    return 0;
+}
+
+int feast_set_solver(feast_ctx* ctx, int kind, int krylov, double inner_tol, int max_inner, int store) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, kind >= 0 && kind <= 2, 2, "unknown solver kind");
+    ARG_CHECK(ctx, krylov >= 0 && krylov <= 2, 3, "unknown Krylov method");
+    ARG_CHECK(ctx, inner_tol > 0 && inner_tol < 1, 4, "inner_tol must be in (0,1)");
+    ARG_CHECK(ctx, max_inner >= 1, 5, "max_inner must be positive");
+    ctx->solver = kind; ctx->krylov = krylov; ctx->inner_tol = inner_tol; ctx->max_inner = max_inner; ctx->store = store;
+    return 0;
+}
+
+int feast_comm_unique_id(void* id128) {
+    if (!id128) return feast_fail(nullptr, -1, "argument 1 invalid: null id buffer");
+    const NcclApi* api = nccl_api();
+    if (!api) return feast_fail(nullptr, FEAST_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    NcclUid id;
+    int rc = api->GetUniqueId(&id);
+    if (rc) return feast_fail(nullptr, FEAST_ERR_NCCL, "ncclGetUniqueId: %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
+    memcpy(id128, &id, sizeof(id));
+    return 0;
+}
+
+int feast_comm_init(feast_ctx* ctx, int nranks, int rank, const void* id128) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, nranks >= 1, 2, "nranks must be positive");
+    ARG_CHECK(ctx, rank >= 0 && rank < nranks, 3, "rank out of range");
+    FEAST_TRY(bind_device(ctx));
+    ctx->nranks = nranks; ctx->rank = rank;
+    if (nranks > 1) {
+        ARG_CHECK(ctx, id128 != nullptr, 4, "null unique id");
+        const NcclApi* api = nccl_api();
+        if (!api) return feast_fail(ctx, FEAST_ERR_NCCL, "libnccl.so.2 could not be loaded");
+        NcclUid id;
+        memcpy(&id, id128, sizeof(id));
+        int rc = api->CommInitRank(&ctx->nccl_comm, nranks, id, rank);
+        if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclCommInitRank: %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
+    }
+    for (size_t k = 0; k < ctx->owner.size(); ++k) ctx->owner[k] = (int)(k % nranks);
+    return 0;
+}
+
+int feast_set_node_owners(feast_ctx* ctx, int nnodes, const int* owner) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, nnodes == (int)ctx->znodes.size(), 2, "nnodes differs from the contour");
+    for (int k = 0; k < nnodes; ++k) {
+        const int o = owner ? owner[k] : k % ctx->nranks;
+        ARG_CHECK(ctx, o >= 0 && o < ctx->nranks, 3, "owner rank out of range");
+        ctx->owner[k] = o;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------- subspace
+int feast_set_subspace(feast_ctx* ctx, int64_t n, int m0, const feast_c128* X, int64_t ldx) {
+    FEAST_TRY(check_ready(ctx, false));
+    ARG_CHECK(ctx, n == ctx->n, 2, "Incorrect dimensions of X, must match A");  // src/feast.jl:15-16
+    ARG_CHECK(ctx, m0 >= 1 && m0 <= n, 3, "m0 out of range");
+    ARG_CHECK(ctx, X != nullptr, 4, "null X");
+    ARG_CHECK(ctx, ldx >= n, 5, "ldx < n");
+    if (ctx->m0 != m0) {
+        free_blocks(ctx);
+        ctx->m0 = m0;
+        FEAST_TRY(dev_alloc(ctx, &ctx->stage, (size_t)n * m0));
+        FEAST_TRY(dev_alloc(ctx, &ctx->small_d, (size_t)4 * m0 * m0 + 16 * (size_t)m0 + 64));
+        // reduction scratch: split-K Gram partials (2*148 slices of m0 x m0) or SpMM/col-dot partials
+        size_t red = std::max((size_t)2 * kNumSMs * m0 * m0 * sizeof(c128), spmm_partials_bytes(m0));
+        red = std::max(red, (size_t)kNumSMs * 4 * 3 * (size_t)std::max(m0, 256) * sizeof(double));
+        red = std::max(red, (size_t)1 << 20);
+        FEAST_TRY(dev_alloc(ctx, &ctx->red_d, red / sizeof(double)));
+        ctx->red_bytes = red;
+        FEAST_TRY(ensure_pinned(ctx, sizeof(hc128) * ((size_t)4 * m0 * m0 + 16 * m0) + 4096));
+    }
+    FEAST_TRY(ensure_block(ctx, ctx->Q));
+    FEAST_TRY(ensure_block(ctx, ctx->X));
+    FEAST_TRY(ensure_block(ctx, ctx->R));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->stage, sizeof(c128) * n, X, sizeof(c128) * ldx, sizeof(c128) * n, m0,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    FEAST_TRY(launch_colmajor_to_rowmajor(ctx, n, m0, ctx->stage, n, ctx->Q.p));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->X.p, ctx->Q.p, sizeof(c128) * n * m0, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int feast_get_X(feast_ctx* ctx, feast_c128* X, int64_t ldx) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, X != nullptr, 2, "null X");
+    ARG_CHECK(ctx, ldx >= ctx->n, 3, "ldx < n");
+    return download_block(ctx, ctx->X, X, ldx);
+}
+int feast_get_Q(feast_ctx* ctx, feast_c128* Q, int64_t ldq) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, Q != nullptr, 2, "null Q");
+    ARG_CHECK(ctx, ldq >= ctx->n, 3, "ldq < n");
+    return download_block(ctx, ctx->Q, Q, ldq);
+}
+int feast_get_R(feast_ctx* ctx, feast_c128* R, int64_t ldr) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, R != nullptr, 2, "null R");
+    ARG_CHECK(ctx, ldr >= ctx->n, 3, "ldr < n");
+    return download_block(ctx, ctx->R, R, ldr);
+}
+
+// ------------------------------------------------------------------------- phases
+int feast_project(feast_ctx* ctx, feast_c128* Aq, feast_c128* Bq) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, Aq != nullptr, 2, "null Aq");
+    if (ctx->problem == FEAST_PROBLEM_POLYNOMIAL)
+        return feast_fail(ctx, FEAST_ERR_STATE, "feast_project applies to linear problems; use feast_beyn_reduce");
+    if (ctx->problem == FEAST_PROBLEM_GENERALIZED) ARG_CHECK(ctx, Bq != nullptr, 3, "null Bq");
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    PhaseTimer tm(ctx, 0);
+    FEAST_TRY(orthonormalize(ctx, ctx->Q, nullptr));                       // feast.jl:41 / :117
+    FEAST_TRY(ensure_block(ctx, ctx->W1));
+    c128* G_d = ctx->small_d;
+    FEAST_TRY(apply_slot(ctx, 0, ctx->Q.p, ctx->R.p));                     // R = A Q      feast.jl:42
+    FEAST_TRY(launch_gram(ctx, n, m, ctx->Q.p, ctx->R.p, G_d));            // Aq = Q' R    feast.jl:43
+    CUDA_TRY(ctx, cudaMemcpyAsync(Aq, G_d, sizeof(c128) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
+    if (Bq) {
+        c128* G2_d = ctx->small_d + (size_t)m * m;
+        FEAST_TRY(apply_slot(ctx, 1, ctx->Q.p, ctx->W1.p));                // R = B Q      feast.jl:120
+        FEAST_TRY(launch_gram(ctx, n, m, ctx->Q.p, ctx->W1.p, G2_d));      // Bq = Q' R    feast.jl:121
+        CUDA_TRY(ctx, cudaMemcpyAsync(Bq, G2_d, sizeof(c128) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    tm.stop();
+    return 0;
+}
+
+int feast_recover_residual(feast_ctx* ctx, const feast_c128* Xq, const feast_c128* lambda, double* res) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, Xq != nullptr, 2, "null Xq");
+    ARG_CHECK(ctx, lambda != nullptr, 3, "null lambda");
+    ARG_CHECK(ctx, res != nullptr, 4, "null res");
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    PhaseTimer tm(ctx, 1);
+    c128* M_d = ctx->small_d;
+    c128* lam_d = ctx->small_d + (size_t)2 * m * m;
+    double* nrm_d = (double*)(ctx->small_d + (size_t)3 * m * m);
+    double* fro_d = nrm_d + m;
+    CUDA_TRY(ctx, cudaMemcpyAsync(M_d, Xq, sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(lam_d, lambda, sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
+    FEAST_TRY(launch_update(ctx, n, m, ctx->Q.p, M_d, ctx->X.p));          // X = Q Xq            feast.jl:48
+    FEAST_TRY(launch_colnorm2(ctx, n, m, ctx->X.p, nrm_d));
+    FEAST_TRY(launch_colnormalize(ctx, n, m, ctx->X.p, nrm_d));            // x_j /= ||x_j||      utils.jl:113
+    double* hres = (double*)ctx->pinned;
+    if (ctx->problem != FEAST_PROBLEM_POLYNOMIAL) {
+        FEAST_TRY(apply_slot(ctx, 0, ctx->X.p, ctx->R.p));                 // R = A X
+        const c128* BX = ctx->X.p;
+        // after build_union an identity B is an OP_CSR slot with unit diagonal: skip the SpMM
+        const bool b_identity = (ctx->problem == FEAST_PROBLEM_STANDARD);
+        if (!b_identity) {
+            FEAST_TRY(ensure_block(ctx, ctx->W1));
+            FEAST_TRY(apply_slot(ctx, 1, ctx->X.p, ctx->W1.p));
+            BX = ctx->W1.p;
+        }
+        FEAST_TRY(launch_residual_combine(ctx, n, m, ctx->R.p, BX, lam_d)); // R_j = (A - l_j B) x_j  utils.jl:114
+        FEAST_TRY(launch_colnorm2(ctx, n, m, ctx->R.p, nrm_d));            // res_j = ||R_j||      utils.jl:168
+        CUDA_TRY(ctx, cudaMemcpyAsync(hres, nrm_d, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int j = 0; j < m; ++j) res[j] = std::sqrt(hres[j]);
+    } else {
+        if (ctx->storage_dense) {
+            // R = sum_i (A_i X) diag(l^i)
+            FEAST_TRY(ensure_block(ctx, ctx->W1));
+            std::vector<hc128> pw(m, hc128(1, 0));
+            c128* pw_d = ctx->small_d + (size_t)m * m;
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->R.p, 0, sizeof(c128) * n * m, ctx->stream));
+            for (int s = 0; s < ctx->nslots; ++s) {
+                FEAST_TRY(apply_slot(ctx, s, ctx->X.p, ctx->W1.p));
+                CUDA_TRY(ctx, cudaMemcpyAsync(pw_d, pw.data(), sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
+                // R += W1 * diag(pw): accumulate with X := W1, Y := 0-block trick -> use first_pass form
+                FEAST_TRY(launch_accumulate(ctx, n, m, nullptr, ctx->W1.p, pw_d, ctx->R.p, nullptr, hc128(0, 0), true));
+                CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+                for (int j = 0; j < m; ++j) pw[j] *= hc128(lambda[j].re, lambda[j].im);
+            }
+            const c128* D[FEAST_MAX_SLOTS];
+            int kinds[FEAST_MAX_SLOTS];
+            for (int s = 0; s < ctx->nslots; ++s) { D[s] = ctx->ops[s].dense; kinds[s] = ctx->ops[s].kind; }
+            FEAST_TRY(launch_poly_fro_dense(ctx, n, m, ctx->nslots, D, kinds, lam_d, fro_d));
+        } else {
+            const double* rv[FEAST_MAX_SLOTS];
+            const c128* cv[FEAST_MAX_SLOTS];
+            for (int s = 0; s < ctx->nslots; ++s) { rv[s] = ctx->ops[s].uvals_r; cv[s] = ctx->ops[s].uvals_c; }
+            FEAST_TRY(launch_poly_residual(ctx, n, m, ctx->nslots, ctx->u_rowptr, ctx->u_col, ctx->unnz, rv, cv, lam_d,
+                                           ctx->X.p, ctx->R.p, fro_d));   // R_j = T(l_j) x_j   utils.jl:107
+        }
+        FEAST_TRY(launch_colnorm2(ctx, n, m, ctx->R.p, nrm_d));
+        CUDA_TRY(ctx, cudaMemcpyAsync(hres, nrm_d, sizeof(double) * 2 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int j = 0; j < m; ++j) res[j] = std::sqrt(hres[j]) / std::sqrt(hres[m + j]);  // utils.jl:154
+    }
+    tm.stop();
+    return 0;
+}
+
+int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass, feast_stats* stats) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, lambda != nullptr || first_pass, 2, "null lambda");
+    if (ctx->znodes.empty()) return feast_fail(ctx, FEAST_ERR_STATE, "feast_set_contour has not been called");
+    if (first_pass && ctx->problem != FEAST_PROBLEM_POLYNOMIAL)
+        return feast_fail(ctx, -3, "argument 3 invalid: first_pass applies to polynomial problems only");
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    const bool poly = ctx->problem == FEAST_PROBLEM_POLYNOMIAL;
+    const int solver = effective_solver(ctx);
+    const int method = effective_krylov(ctx);
+    if (solver == FEAST_SOLVER_KRYLOV && ctx->storage_dense)
+        return feast_fail(ctx, FEAST_ERR_STATE, "Krylov inner solves need sparse operators");
+    FEAST_TRY(ensure_block(ctx, ctx->W1));
+    if (poly) FEAST_TRY(ensure_block(ctx, ctx->Q1));
+    if (solver == FEAST_SOLVER_KRYLOV) FEAST_TRY(ensure_krylov_work(ctx, method));
+    feast_stats st;
+    memset(&st, 0, sizeof(st));
+    cudaEvent_t e0, e1, e2, e3;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    PhaseTimer tm(ctx, 2);
+    int rc_final = 0;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->Q.p, 0, sizeof(c128) * n * m, ctx->stream));           // feast.jl:58
+    if (poly) CUDA_TRY(ctx, cudaMemsetAsync(ctx->Q1.p, 0, sizeof(c128) * n * m, ctx->stream)); // nlfeast.jl:32-33
+    const int nnodes = (int)ctx->znodes.size();
+    if (ctx->store && (int)ctx->stored.size() != nnodes) ctx->stored.resize(nnodes);
+    c128* d_d = ctx->small_d + (size_t)3 * m * m;
+    std::vector<hc128> d(m);
+    hc128 coef[FEAST_MAX_SLOTS];
+    const c128* rhs = first_pass ? ctx->X.p : ctx->R.p;
+    for (int k = 0; k < nnodes; ++k) {
+        if (ctx->owner[k] != ctx->rank) continue;
+        st.nodes_local++;
+        const hc128 z = ctx->znodes[k], w = ctx->zweights[k];
+        node_coefs(ctx, z, coef);
+        for (int j = 0; j < m; ++j)
+            d[j] = first_pass ? w : w / (z - hc128(lambda[j].re, lambda[j].im));              // feast.jl:60,69
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_d, d.data(), sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
+        cudaEventRecord(e0, ctx->stream);
+        if (solver == FEAST_SOLVER_DENSE_LU) {
+            DenseLU* f;
+            DenseLU scratch;
+            bool need_factor = true;
+            if (ctx->store) {
+                f = &ctx->stored[k];
+                need_factor = (f->lu == nullptr);
+            } else {
+                if (!ctx->zdense) FEAST_TRY(dev_alloc(ctx, &ctx->zdense, (size_t)n * n));
+                if (!ctx->zpiv) FEAST_TRY(dev_alloc(ctx, &ctx->zpiv, (size_t)2 * n));
+                scratch.lu = ctx->zdense; scratch.ipiv = ctx->zpiv; scratch.perm = ctx->zpiv + n;
+                f = &scratch;
+            }
+            if (need_factor) {
+                int info = 0;
+                FEAST_TRY(factor_dense(ctx, coef, *f, &info));                                // feast.jl:36 / :65 lu
+                if (info && !st.info) st.info = info;
+            }
+            cudaEventRecord(e1, ctx->stream);
+            FEAST_TRY(dense_getrs(ctx, n, f->lu, f->perm, m, rhs, ctx->W1.p, false));         // ldiv!
+        } else {
+            FEAST_TRY(assemble_sparse_Z(ctx, coef, ctx->zvals));
+            cudaEventRecord(e1, ctx->stream);
+            KrylovResult kr;
+            FEAST_TRY(krylov_solve(ctx, method, ctx->zvals, rhs, ctx->W1.p, ctx->inner_tol, ctx->max_inner, &kr));
+            st.inner_iters_total += kr.iters;
+            st.inner_iters_max = std::max(st.inner_iters_max, kr.iters);
+            st.inner_relres_max = std::max(st.inner_relres_max, kr.relres_max);
+            if (!kr.converged) rc_final = FEAST_WARN_INNER_MAXIT;
+        }
+        // Q += (X - Y) diag(w/(z - l))  [feast.jl:68-70] ; polynomial: Q0, Q1 [nlfeast.jl:56-58]
+        FEAST_TRY(launch_accumulate(ctx, n, m, ctx->X.p, ctx->W1.p, d_d, ctx->Q.p, poly ? ctx->Q1.p : nullptr, z,
+                                    first_pass != 0));
+        cudaEventRecord(e2, ctx->stream);
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // d (host vector) is reused next node
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        st.t_factor_ms += a;
+        st.t_solve_ms += b;
+    }
+    if (ctx->nranks > 1) {                                                                     // NC1
+        const NcclApi* api = nccl_api();
+        cudaEventRecord(e0, ctx->stream);
+        int rc = api->AllReduce(ctx->Q.p, ctx->Q.p, (size_t)2 * n * m, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
+        if (!rc && poly)
+            rc = api->AllReduce(ctx->Q1.p, ctx->Q1.p, (size_t)2 * n * m, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
+        if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclAllReduce: %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
+        cudaEventRecord(e3, ctx->stream);
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        float c = 0;
+        cudaEventElapsedTime(&c, e0, e3);
+        st.t_reduce_ms = c;
+    }
+    st.t_total_ms = tm.stop();
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    if (stats) *stats = st;
+    if (st.info) return feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d of a shifted factorisation", st.info);
+    if (rc_final == FEAST_WARN_INNER_MAXIT)
+        feast_fail(ctx, FEAST_WARN_INNER_MAXIT, "Krylov inner solve stopped at max_inner=%d (relres %.3e)", ctx->max_inner,
+                   st.inner_relres_max);
+    return rc_final;
+}
+
+int feast_orthonormalize_X(feast_ctx* ctx) {
+    FEAST_TRY(check_ready(ctx, true));
+    FEAST_TRY(orthonormalize(ctx, ctx->X, nullptr));  // nlfeast.jl:12-13
+    return 0;
+}
+
+int feast_beyn_reduce(feast_ctx* ctx, feast_c128* Rf, feast_c128* G1) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, Rf != nullptr, 2, "null Rf");
+    ARG_CHECK(ctx, G1 != nullptr, 3, "null G1");
+    if (!ctx->Q1.p) return feast_fail(ctx, FEAST_ERR_STATE, "feast_contour_apply (polynomial) has not produced Q1 yet");
+    const int m = ctx->m0;
+    PhaseTimer tm(ctx, 0);
+    std::vector<hc128> Rtot;
+    FEAST_TRY(orthonormalize(ctx, ctx->Q, &Rtot));                  // Q0 = U Rtot  (tall svd! of utils.jl:70 -> QR + small SVD)
+    memcpy(Rf, Rtot.data(), sizeof(hc128) * m * m);
+    c128* G_d = ctx->small_d;
+    FEAST_TRY(launch_gram(ctx, ctx->n, m, ctx->Q.p, ctx->Q1.p, G_d));  // U' Q1        utils.jl:71
+    CUDA_TRY(ctx, cudaMemcpyAsync(G1, G_d, sizeof(c128) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
+    tm.stop();
+    return 0;
+}
+
+// ------------------------------------------------------------------------- plugin path
+int feast_factorize(feast_ctx* ctx, const feast_c128* coef, int ncoef, feast_factor** out) {
+    FEAST_TRY(check_ready(ctx, false));
+    ARG_CHECK(ctx, coef != nullptr, 2, "null coefficients");
+    ARG_CHECK(ctx, ncoef >= 1 && ncoef <= ctx->nslots, 3, "ncoef out of range");
+    ARG_CHECK(ctx, out != nullptr, 4, "null output");
+    hc128 cf[FEAST_MAX_SLOTS];
+    for (int s = 0; s < FEAST_MAX_SLOTS; ++s) cf[s] = s < ncoef ? hc128(coef[s].re, coef[s].im) : hc128(0, 0);
+    feast_factor* F = new feast_factor();
+    F->kind = effective_solver(ctx);
+    if (F->kind == FEAST_SOLVER_DENSE_LU) {
+        if (!ctx->red_d) {  // getrf scratch when no subspace has been set yet
+            FEAST_TRY(dev_alloc(ctx, &ctx->red_d, ((size_t)1 << 20) / sizeof(double)));
+            ctx->red_bytes = (size_t)1 << 20;
+        }
+        int info = 0;
+        int rc = factor_dense(ctx, cf, F->lu, &info);
+        if (rc) { delete F; return rc; }
+        if (info) {
+            dev_free(F->lu.lu); dev_free(F->lu.ipiv); dev_free(F->lu.perm);
+            delete F;
+            return feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d", info);
+        }
+    } else {
+        int rc = dev_alloc(ctx, &F->zvals, ctx->unnz);
+        if (!rc) rc = assemble_sparse_Z(ctx, cf, F->zvals);
+        if (rc) { delete F; return rc; }
+        F->symmetric = ctx->all_symmetric;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = F;
+    return 0;
+}
+
+int feast_solve(feast_ctx* ctx, const feast_factor* F, int64_t n, int nrhs, const feast_c128* Bm, int64_t ldb,
+                feast_c128* Y, int64_t ldy, int conj_transpose) {
+    FEAST_TRY(check_ready(ctx, false));
+    ARG_CHECK(ctx, F != nullptr, 2, "null factor");
+    ARG_CHECK(ctx, n == ctx->n, 3, "dimension mismatch");
+    ARG_CHECK(ctx, nrhs >= 1, 4, "nrhs must be positive");
+    ARG_CHECK(ctx, Bm != nullptr, 5, "null right-hand side");
+    ARG_CHECK(ctx, ldb >= n, 6, "ldb < n");
+    ARG_CHECK(ctx, Y != nullptr, 7, "null solution");
+    ARG_CHECK(ctx, ldy >= n, 8, "ldy < n");
+    if (ctx->m0 != nrhs) {
+        // the block workspace is sized by m0: (re)size it through a zero subspace of the right width
+        std::vector<hc128> zero((size_t)n * nrhs, hc128(0, 0));
+        FEAST_TRY(feast_set_subspace(ctx, n, nrhs, (const feast_c128*)zero.data(), n));
+    }
+    FEAST_TRY(ensure_block(ctx, ctx->W1));
+    FEAST_TRY(ensure_block(ctx, ctx->W2));
+    const int m = nrhs;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->stage, sizeof(c128) * n, Bm, sizeof(c128) * ldb, sizeof(c128) * n, m,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    FEAST_TRY(ensure_block(ctx, ctx->R));
+    c128* rhs = ctx->R.p;
+    FEAST_TRY(launch_colmajor_to_rowmajor(ctx, n, m, ctx->stage, n, rhs));
+    int rc_final = 0;
+    if (F->kind == FEAST_SOLVER_DENSE_LU) {
+        FEAST_TRY(dense_getrs(ctx, n, F->lu.lu, F->lu.perm, m, rhs, ctx->W1.p, conj_transpose != 0));
+    } else {
+        if (conj_transpose && !F->symmetric)
+            return feast_fail(ctx, FEAST_ERR_STATE, "adjoint Krylov solve needs a symmetric operator in this build");
+        const int method = effective_krylov(ctx);
+        FEAST_TRY(ensure_krylov_work(ctx, method));
+        KrylovResult kr;
+        if (conj_transpose) {
+            // Z symmetric: Z^H = conj(Z)  ->  Z^H y = b  <=>  Z conj(y) = conj(b)
+            return feast_fail(ctx, FEAST_ERR_STATE, "adjoint Krylov solve is not implemented yet");
+        }
+        FEAST_TRY(krylov_solve(ctx, method, F->zvals, rhs, ctx->W1.p, ctx->inner_tol, ctx->max_inner, &kr));
+        if (!kr.converged) rc_final = FEAST_WARN_INNER_MAXIT;
+    }
+    FEAST_TRY(launch_rowmajor_to_colmajor(ctx, n, m, ctx->W1.p, ctx->stage, n));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(Y, sizeof(c128) * ldy, ctx->stage, sizeof(c128) * n, sizeof(c128) * n, m,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc_final;
+}
+
+int feast_factor_free(feast_ctx* ctx, feast_factor* F) {  // finalize!(F), src/utils.jl:173
+    if (!F) return 0;
+    if (ctx) cudaSetDevice(ctx->device);
+    dev_free(F->lu.lu); dev_free(F->lu.ipiv); dev_free(F->lu.perm);
+    dev_free(F->zvals);
+    delete F;
+    return 0;
+}
+
+// ------------------------------------------------------------------------- kernel-level entries
+int feast_apply_operator(feast_ctx* ctx, int slot, int which, feast_c128* Y, int64_t ldy, int reps, float* ms) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, slot >= 0 && slot < ctx->nslots, 2, "slot out of range");
+    ARG_CHECK(ctx, which == 0 || which == 1, 3, "which must be 0 (Q) or 1 (X)");
+    if (reps < 1) reps = 1;
+    const c128* V = which == 0 ? ctx->Q.p : ctx->X.p;
+    FEAST_TRY(apply_slot(ctx, slot, V, ctx->R.p));  // warm-up / result
+    if (ms) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        for (int r = 0; r < reps; ++r) FEAST_TRY(apply_slot(ctx, slot, V, ctx->R.p));
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+        float t = 0;
+        cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1);
+        *ms = t / reps;
+    }
+    if (Y) {
+        ARG_CHECK(ctx, ldy >= ctx->n, 5, "ldy < n");
+        return download_block(ctx, ctx->R, Y, ldy);
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int feast_sync(feast_ctx* ctx) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    FEAST_TRY(bind_device(ctx));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int64_t feast_launch_count(const feast_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int feast_phase_times(feast_ctx* ctx, double* ms3, int reset) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    if (ms3) for (int i = 0; i < 3; ++i) ms3[i] = ctx->phase_ms[i];
+    if (reset) for (int i = 0; i < 3; ++i) ctx->phase_ms[i] = 0.0;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,179 @@
+// Shared definitions for libfeast_cuda.so (sm_100a only; no other backend).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <complex>
+
+#include "../../include/feast_cuda.h"
+
+typedef double2 c128;                       // interleaved (re, im) == Julia ComplexF64
+typedef std::complex<double> hc128;         // host-side twin
+
+// ------------------------------------------------------------------ complex helpers
+__host__ __device__ __forceinline__ c128 cmake(double r, double i) { return make_double2(r, i); }
+__host__ __device__ __forceinline__ c128 cadd(c128 a, c128 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ c128 csub(c128 a, c128 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ c128 cmul(c128 a, c128 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ c128 cconj(c128 a) { return make_double2(a.x, -a.y); }
+__host__ __device__ __forceinline__ c128 cscale(double s, c128 a) { return make_double2(s * a.x, s * a.y); }
+// acc += a*b  (4 FMAs)
+__device__ __forceinline__ void cfma(c128& acc, c128 a, c128 b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+// acc += conj(a)*b
+__device__ __forceinline__ void cfma_conj(c128& acc, c128 a, c128 b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+// acc += s*b, s real
+__device__ __forceinline__ void rfma(c128& acc, double s, c128 b) {
+    acc.x = fma(s, b.x, acc.x); acc.y = fma(s, b.y, acc.y);
+}
+__host__ __device__ __forceinline__ c128 cdiv(c128 a, c128 b) {
+    // Smith's algorithm (robust against overflow of |b|^2)
+    if (fabs(b.x) >= fabs(b.y)) {
+        double r = b.y / b.x, d = b.x + b.y * r;
+        return make_double2((a.x + a.y * r) / d, (a.y - a.x * r) / d);
+    } else {
+        double r = b.x / b.y, d = b.x * r + b.y;
+        return make_double2((a.x * r + a.y) / d, (a.y * r - a.x) / d);
+    }
+}
+__host__ __device__ __forceinline__ double cabs2(c128 a) { return a.x * a.x + a.y * a.y; }
+__host__ __device__ __forceinline__ double cabs1(c128 a) { return fabs(a.x) + fabs(a.y); }  // LAPACK izamax measure
+
+// ------------------------------------------------------------------ operator storage
+enum { OP_NONE = 0, OP_IDENTITY = 1, OP_DENSE = 2, OP_CSR = 3 };
+
+struct HostCSR {            // host copy kept until the union pattern is built
+    int64_t n = 0, nnz = 0;
+    std::vector<int64_t> rowptr;
+    std::vector<int> col;
+    std::vector<hc128> val;
+    bool is_complex = false;
+    bool symmetric = false; // S == S^T (values, not conjugated)
+};
+
+struct Operator {
+    int kind = OP_NONE;
+    int64_t n = 0;
+    bool is_complex = false;
+    bool symmetric = false;
+    c128* dense = nullptr;     // OP_DENSE: column-major n x n (device)
+    HostCSR host;              // OP_CSR before feast_set_problem
+    double* uvals_r = nullptr; // OP_CSR/IDENTITY after set_problem: values on the union pattern (real ...)
+    c128*   uvals_c = nullptr; // ... or complex
+};
+
+struct BlockVec {            // n x m0 complex block, ROW-MAJOR (m0 contiguous): the
+    c128* p = nullptr;       // layout the CSR SpMM gathers coalesced 16*m0-byte rows from
+};
+
+struct DenseLU {             // one stored factorisation (column-major, LAPACK getrf layout)
+    c128* lu = nullptr;
+    int*  ipiv = nullptr;    // device, 0-based absolute row indices (LAPACK interchange sequence)
+    int*  perm = nullptr;    // device, perm[i] = source row of permuted row i
+    int64_t n = 0;
+};
+
+struct feast_factor {        // fine-grained plugin handle
+    int kind = 0;            // FEAST_SOLVER_DENSE_LU / FEAST_SOLVER_KRYLOV
+    DenseLU lu;
+    c128* zvals = nullptr;   // Krylov: assembled union-pattern values
+    bool symmetric = false;
+};
+
+struct NcclApi;              // nccl_dl.cpp
+
+struct feast_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // problem
+    int problem = FEAST_PROBLEM_STANDARD;
+    int nslots = 0;
+    bool problem_ready = false;
+    bool storage_dense = false;
+    int64_t n = 0;
+    Operator ops[FEAST_MAX_SLOTS];
+    // union sparsity pattern of all sparse slots (CSR, 32-bit columns)
+    int64_t unnz = 0;
+    int* u_rowptr = nullptr;
+    int* u_col = nullptr;
+    bool all_symmetric = false;
+    c128* zvals = nullptr;        // assembled shifted operator on the union pattern
+    c128* zdense = nullptr;       // assembled dense shifted operator (n x n col-major)
+    int*  zpiv = nullptr;
+
+    // contour
+    std::vector<hc128> znodes, zweights;
+    std::vector<int> owner;       // node -> rank
+    // solver
+    int solver = FEAST_SOLVER_AUTO, krylov = FEAST_KRYLOV_AUTO;
+    double inner_tol = 1e-10;
+    int max_inner = 5000;
+    int store = 0;
+    std::vector<DenseLU> stored;  // per node (only local nodes populated)
+    bool panel_attr_set = false;
+    int dense_threshold = 6000;   // sparse problems up to this n are solved by dense LU
+
+    // subspace blocks
+    int m0 = 0;
+    BlockVec Q, X, R, Q1, W1, W2;       // Q1: second moment accumulator (polynomial)
+    BlockVec kx, kr, kp, kq, ks, kt, kv, krh; // Krylov work
+    c128* stage = nullptr;        // n x m0 column-major staging (uploads / downloads)
+    c128* small_d = nullptr;      // device scratch for m0 x m0 matrices (4 of them) + scalars
+    double* red_d = nullptr;      // reduction partials
+    size_t red_bytes = 0;
+    void* pinned = nullptr;       // pinned host scratch
+    size_t pinned_bytes = 0;
+    std::vector<hc128> orthR;     // accumulated R factor of the last orthonormalisation (m0 x m0, col-major)
+
+    // multi-GPU
+    int nranks = 1, rank = 0;
+    void* nccl_comm = nullptr;
+
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double phase_ms[3] = {0, 0, 0};
+};
+
+// ------------------------------------------------------------------ error plumbing
+extern std::string g_last_error;
+int feast_fail(feast_ctx* ctx, int code, const char* fmt, ...);
+
+#define CUDA_TRY(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            int code__ = (e__ == cudaErrorMemoryAllocation) ? FEAST_ERR_OOM : FEAST_ERR_CUDA; \
+            return feast_fail(ctx, code__, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+                              cudaGetErrorString(e__));                                       \
+        }                                                                                     \
+    } while (0)
+
+#define FEAST_TRY(call)            \
+    do {                           \
+        int rc__ = (call);         \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+#define KLAUNCH_CHECK(ctx)                                                                     \
+    do {                                                                                       \
+        (ctx)->launches++;                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                                  \
+        if (e__ != cudaSuccess)                                                                \
+            return feast_fail(ctx, FEAST_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, \
+                              __LINE__, cudaGetErrorString(e__));                              \
+    } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this

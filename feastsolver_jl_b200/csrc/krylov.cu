@@ -1,0 +1,367 @@
+// K5: pseudo-block Krylov inner solves for the sparse shifted systems
+//   (A - z_k B) Y = R      (src/feast.jl:61-66,138-143 via linsolve!, src/utils.jl:175-179)
+// All m0 right-hand sides advance in lock step and share ONE SpMM per iteration; the
+// recurrences (alpha_j, beta_j, ...) are per column and live on the device, so the host
+// only reads a convergence flag every few iterations.  COCG is used when every operator
+// slot is (complex-)symmetric -- A - zB is then complex symmetric -- BiCGStab otherwise
+// (the reference's own inexact-solve precedent is bicgstabl, src/nlfeast.jl:106,139).
+// In residual-inverse-iteration form the solve error is relative to the shrinking ||R||,
+// which is what lets an inexact inner solve reproduce the reference's eigen-residuals.
+#include "kernels.cuh"
+
+namespace {
+
+struct KryScal {         // device scalars, m entries each
+    c128* rho; c128* mu; c128* alpha; c128* beta; c128* omega; c128* tmp1; c128* tmp2;
+    double* bn2; double* rn2;
+    int* active;         // per column
+    int* nactive;        // single int
+    double* relmax;      // single double: max_j ||r_j|| / ||b_j||
+};
+
+__global__ void kry_init_scalars(int m, KryScal s, double tol2) {
+    // after rho = <r,r>, bn2 = ||b||^2 were reduced
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const int act = (s.bn2[j] > 0.0) ? 1 : 0;   // zero right-hand side -> solution 0
+        s.active[j] = act;
+        s.rn2[j] = s.bn2[j];
+        s.alpha[j] = cmake(1.0, 0.0);
+        s.omega[j] = cmake(1.0, 0.0);
+        s.beta[j] = cmake(0.0, 0.0);
+        if (act) atomicAdd(&cnt, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *s.nactive = cnt; *s.relmax = cnt ? 1.0 : 0.0; }
+}
+
+// alpha = rho / mu (frozen columns get alpha = 0)
+__global__ void cocg_alpha_kernel(int m, KryScal s) {
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        c128 a = cmake(0.0, 0.0);
+        if (s.active[j]) {
+            const c128 mu = s.mu[j];
+            if (cabs2(mu) > 0.0 && isfinite(mu.x) && isfinite(mu.y)) a = cdiv(s.rho[j], mu);
+            else s.active[j] = 0;  // breakdown: freeze the column
+        }
+        s.alpha[j] = a;
+    }
+}
+
+// x += alpha p ; r -= alpha q ; partials of <r,r> (unconjugated) and ||r||^2
+__global__ void __launch_bounds__(256)
+cocg_update_kernel(int64_t n, int m, c128* __restrict__ x, c128* __restrict__ r, const c128* __restrict__ p,
+                   const c128* __restrict__ q, KryScal s, double* __restrict__ partials) {
+    extern __shared__ double sm[];  // [256][3]
+    int cw = 1;
+    while (cw < m && cw < 256) cw <<= 1;
+    const int rpp = 256 / cw, cj = threadIdx.x % cw, rr = threadIdx.x / cw;
+    for (int jbase = 0; jbase < m; jbase += cw) {
+        const int j = jbase + cj;
+        double re = 0.0, im = 0.0, nn = 0.0;
+        if (j < m) {
+            const c128 a = s.alpha[j];
+            const bool act = s.active[j] != 0;
+            for (int64_t i = (int64_t)blockIdx.x * rpp + rr; i < n; i += (int64_t)gridDim.x * rpp) {
+                const int64_t t = i * m + j;
+                c128 rv = r[t];
+                if (act) {
+                    c128 xv = x[t];
+                    cfma(xv, a, __ldg(p + t));
+                    x[t] = xv;
+                    const c128 na = cmake(-a.x, -a.y);
+                    cfma(rv, na, __ldg(q + t));
+                    r[t] = rv;
+                }
+                re = fma(rv.x, rv.x, re); re = fma(-rv.y, rv.y, re);
+                im = fma(2.0 * rv.x, rv.y, im);
+                nn = fma(rv.x, rv.x, nn); nn = fma(rv.y, rv.y, nn);
+            }
+        }
+        sm[3 * threadIdx.x] = re; sm[3 * threadIdx.x + 1] = im; sm[3 * threadIdx.x + 2] = nn;
+        __syncthreads();
+        if (rr == 0 && j < m) {
+            for (int k = 1; k < rpp; ++k) {
+                re += sm[3 * (k * cw + cj)]; im += sm[3 * (k * cw + cj) + 1]; nn += sm[3 * (k * cw + cj) + 2];
+            }
+            double* o = partials + (int64_t)blockIdx.x * 3 * m + 3 * j;
+            o[0] = re; o[1] = im; o[2] = nn;
+        }
+        __syncthreads();
+    }
+}
+
+// reduce partials -> rho', ||r||^2 ; beta = rho'/rho ; convergence bookkeeping
+__global__ void cocg_beta_kernel(int m, int nblocks, const double* __restrict__ partials, KryScal s, double tol2) {
+    __shared__ int cnt;
+    __shared__ double rmax;
+    if (threadIdx.x == 0) { cnt = 0; rmax = 0.0; }
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        double re = 0.0, im = 0.0, nn = 0.0;
+        for (int b = 0; b < nblocks; ++b) {
+            const double* o = partials + (int64_t)b * 3 * m + 3 * j;
+            re += o[0]; im += o[1]; nn += o[2];
+        }
+        s.rn2[j] = nn;
+        c128 beta = cmake(0.0, 0.0);
+        if (s.active[j]) {
+            const c128 rho_new = cmake(re, im), rho_old = s.rho[j];
+            if (nn <= tol2 * s.bn2[j]) s.active[j] = 0;
+            else if (cabs2(rho_old) > 0.0 && isfinite(re) && isfinite(im)) beta = cdiv(rho_new, rho_old);
+            else s.active[j] = 0;
+            s.rho[j] = rho_new;
+        }
+        s.beta[j] = beta;
+        if (s.active[j]) atomicAdd(&cnt, 1);
+        const double rel = s.bn2[j] > 0.0 ? sqrt(nn / s.bn2[j]) : 0.0;
+        // atomicMax on doubles via CAS on the bit pattern (values are non-negative)
+        unsigned long long* addr = (unsigned long long*)&rmax;
+        unsigned long long old = *addr, assumed;
+        do {
+            assumed = old;
+            if (__longlong_as_double((long long)assumed) >= rel) break;
+            old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(rel));
+        } while (assumed != old);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *s.nactive = cnt; *s.relmax = rmax; }
+}
+
+// p = r + beta p (active columns only)
+__global__ void cocg_p_kernel(int64_t total, int m, c128* __restrict__ p, const c128* __restrict__ r, KryScal s) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % m);
+        if (!s.active[j]) continue;
+        c128 v = __ldg(r + t);
+        cfma(v, s.beta[j], p[t]);
+        p[t] = v;
+    }
+}
+
+// ----------------------------------------------------------------------------- BiCGStab pieces
+// beta = (rho'/rho)(alpha/omega); rho = rho'   [rho' in tmp1]
+__global__ void bicg_beta_kernel(int m, KryScal s) {
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        c128 b = cmake(0.0, 0.0);
+        if (s.active[j]) {
+            const c128 rn = s.tmp1[j], ro = s.rho[j], om = s.omega[j];
+            if (cabs2(ro) > 0.0 && cabs2(om) > 0.0) b = cmul(cdiv(rn, ro), cdiv(s.alpha[j], om));
+            else s.active[j] = 0;
+            s.rho[j] = rn;
+        }
+        s.beta[j] = b;
+    }
+}
+// p = r + beta (p - omega v)
+__global__ void bicg_p_kernel(int64_t total, int m, c128* __restrict__ p, const c128* __restrict__ r,
+                              const c128* __restrict__ v, KryScal s) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % m);
+        if (!s.active[j]) continue;
+        const c128 om = s.omega[j];
+        c128 w = p[t];
+        cfma(w, cmake(-om.x, -om.y), __ldg(v + t));
+        c128 o = __ldg(r + t);
+        cfma(o, s.beta[j], w);
+        p[t] = o;
+    }
+}
+// alpha = rho / <rhat, v>   [<rhat,v> in tmp1]
+__global__ void bicg_alpha_kernel(int m, KryScal s) {
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        c128 a = cmake(0.0, 0.0);
+        if (s.active[j]) {
+            const c128 d = s.tmp1[j];
+            if (cabs2(d) > 0.0 && isfinite(d.x) && isfinite(d.y)) a = cdiv(s.rho[j], d);
+            else s.active[j] = 0;
+        }
+        s.alpha[j] = a;
+    }
+}
+// s = r - alpha v
+__global__ void bicg_s_kernel(int64_t total, int m, c128* __restrict__ sv, const c128* __restrict__ r,
+                              const c128* __restrict__ v, KryScal s) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % m);
+        const c128 a = s.alpha[j];
+        c128 o = __ldg(r + t);
+        cfma(o, cmake(-a.x, -a.y), __ldg(v + t));
+        sv[t] = o;
+    }
+}
+// omega = <t,s>/<t,t>   [<t,s> in tmp1 (conj t), ||t||^2 in rn2 (temporarily)]
+__global__ void bicg_omega_kernel(int m, KryScal s, const double* __restrict__ tt) {
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        c128 o = cmake(0.0, 0.0);
+        if (s.active[j] && tt[j] > 0.0) o = cscale(1.0 / tt[j], s.tmp1[j]);
+        s.omega[j] = o;
+    }
+}
+// x += alpha p + omega s ; r = s - omega t
+__global__ void bicg_xr_kernel(int64_t total, int m, c128* __restrict__ x, c128* __restrict__ r,
+                               const c128* __restrict__ p, const c128* __restrict__ sv, const c128* __restrict__ tv,
+                               KryScal s) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % m);
+        if (!s.active[j]) continue;
+        const c128 a = s.alpha[j], om = s.omega[j];
+        c128 xv = x[t];
+        cfma(xv, a, __ldg(p + t));
+        const c128 sj = __ldg(sv + t);
+        cfma(xv, om, sj);
+        x[t] = xv;
+        c128 rv = sj;
+        cfma(rv, cmake(-om.x, -om.y), __ldg(tv + t));
+        r[t] = rv;
+    }
+}
+// after rn2 = ||r||^2: update active flags / counters
+__global__ void kry_check_kernel(int m, KryScal s, double tol2) {
+    __shared__ int cnt;
+    __shared__ double rmax;
+    if (threadIdx.x == 0) { cnt = 0; rmax = 0.0; }
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const double nn = s.rn2[j];
+        if (s.active[j] && (nn <= tol2 * s.bn2[j] || !isfinite(nn))) s.active[j] = 0;
+        if (s.active[j]) atomicAdd(&cnt, 1);
+        const double rel = s.bn2[j] > 0.0 ? sqrt(nn / s.bn2[j]) : 0.0;
+        unsigned long long* addr = (unsigned long long*)&rmax;
+        unsigned long long old = *addr, assumed;
+        do {
+            assumed = old;
+            if (__longlong_as_double((long long)assumed) >= rel) break;
+            old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(rel));
+        } while (assumed != old);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *s.nactive = cnt; *s.relmax = rmax; }
+}
+
+int ew_grid_k(int64_t total) {
+    int64_t g = (total + 255) / 256, cap = (int64_t)kNumSMs * 16;
+    if (g > cap) g = cap;
+    return (int)(g < 1 ? 1 : g);
+}
+int red_grid_k(int64_t n, int m) {
+    int cw = 1;
+    while (cw < m && cw < 256) cw <<= 1;
+    int rpp = 256 / cw;
+    int64_t need = (n + rpp - 1) / rpp, cap = (int64_t)kNumSMs * 4;
+    return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+KryScal carve_scalars(feast_ctx* ctx) {
+    const int m = ctx->m0;
+    c128* base = ctx->small_d + (size_t)4 * m * m;
+    KryScal s;
+    s.rho = base; s.mu = base + m; s.alpha = base + 2 * m; s.beta = base + 3 * m; s.omega = base + 4 * m;
+    s.tmp1 = base + 5 * m; s.tmp2 = base + 6 * m;
+    s.bn2 = (double*)(base + 7 * m);
+    s.rn2 = s.bn2 + m;
+    s.active = (int*)(base + 8 * m);            // m ints fit in m/4 c128
+    s.nactive = (int*)(base + 9 * m);
+    s.relmax = (double*)(base + 9 * m + 1);
+    return s;
+}
+
+}  // namespace
+
+int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit,
+                 KrylovResult* out) {
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    const int64_t total = n * m;
+    const size_t bytes = sizeof(c128) * total;
+    KryScal s = carve_scalars(ctx);
+    const double tol2 = tol * tol;
+    c128 *x = Y, *r = ctx->kr.p, *p = ctx->kp.p, *q = ctx->kq.p;
+    cudaStream_t st = ctx->stream;
+    struct HostFlag { int nactive; int pad; double relmax; };
+    HostFlag* hf = (HostFlag*)ctx->pinned;
+    const int check_every = 8;
+
+    CUDA_TRY(ctx, cudaMemsetAsync(x, 0, bytes, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(r, Rhs, bytes, cudaMemcpyDeviceToDevice, st));
+    FEAST_TRY(launch_colnorm2(ctx, n, m, r, s.bn2));
+    int iters = 0;
+    const int rgrid = red_grid_k(n, m);
+
+    if (method == FEAST_KRYLOV_COCG) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(p, Rhs, bytes, cudaMemcpyDeviceToDevice, st));
+        FEAST_TRY(launch_coldot(ctx, n, m, r, r, false, s.rho));
+        kry_init_scalars<<<1, 128, 0, st>>>(m, s, tol2);
+        KLAUNCH_CHECK(ctx);
+        while (iters < maxit) {
+            // q = Z p, mu = <p, q>
+            FEAST_TRY(launch_spmm(ctx, n, m, ctx->u_rowptr, ctx->u_col, nullptr, zvals, p, m, q, m, s.mu));
+            cocg_alpha_kernel<<<1, 128, 0, st>>>(m, s);
+            KLAUNCH_CHECK(ctx);
+            cocg_update_kernel<<<rgrid, 256, 768 * sizeof(double), st>>>(n, m, x, r, p, q, s, ctx->red_d);
+            KLAUNCH_CHECK(ctx);
+            cocg_beta_kernel<<<1, 128, 0, st>>>(m, rgrid, ctx->red_d, s, tol2);
+            KLAUNCH_CHECK(ctx);
+            cocg_p_kernel<<<ew_grid_k(total), 256, 0, st>>>(total, m, p, r, s);
+            KLAUNCH_CHECK(ctx);
+            ++iters;
+            if (iters % check_every == 0 || iters == maxit) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(&hf->nactive, s.nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(ctx, cudaMemcpyAsync(&hf->relmax, s.relmax, sizeof(double), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(ctx, cudaStreamSynchronize(st));
+                if (hf->nactive == 0) break;
+            }
+        }
+    } else {
+        c128 *rh = ctx->krh.p, *v = ctx->kv.p, *sv = ctx->ks.p, *tv = ctx->kt.p;
+        CUDA_TRY(ctx, cudaMemcpyAsync(rh, Rhs, bytes, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(p, 0, bytes, st));
+        CUDA_TRY(ctx, cudaMemsetAsync(v, 0, bytes, st));
+        kry_init_scalars<<<1, 128, 0, st>>>(m, s, tol2);
+        KLAUNCH_CHECK(ctx);
+        // rho = 1 initially
+        {
+            std::vector<hc128> ones(m, hc128(1.0, 0.0));
+            CUDA_TRY(ctx, cudaMemcpyAsync(s.rho, ones.data(), sizeof(c128) * m, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        }
+        while (iters < maxit) {
+            FEAST_TRY(launch_coldot(ctx, n, m, rh, r, true, s.tmp1));  // rho' = <rhat, r>
+            bicg_beta_kernel<<<1, 128, 0, st>>>(m, s);
+            KLAUNCH_CHECK(ctx);
+            bicg_p_kernel<<<ew_grid_k(total), 256, 0, st>>>(total, m, p, r, v, s);
+            KLAUNCH_CHECK(ctx);
+            FEAST_TRY(launch_spmm(ctx, n, m, ctx->u_rowptr, ctx->u_col, nullptr, zvals, p, m, v, m, nullptr));
+            FEAST_TRY(launch_coldot(ctx, n, m, rh, v, true, s.tmp1));
+            bicg_alpha_kernel<<<1, 128, 0, st>>>(m, s);
+            KLAUNCH_CHECK(ctx);
+            bicg_s_kernel<<<ew_grid_k(total), 256, 0, st>>>(total, m, sv, r, v, s);
+            KLAUNCH_CHECK(ctx);
+            FEAST_TRY(launch_spmm(ctx, n, m, ctx->u_rowptr, ctx->u_col, nullptr, zvals, sv, m, tv, m, nullptr));
+            FEAST_TRY(launch_coldot(ctx, n, m, tv, sv, true, s.tmp1));
+            FEAST_TRY(launch_colnorm2(ctx, n, m, tv, (double*)s.tmp2));
+            bicg_omega_kernel<<<1, 128, 0, st>>>(m, s, (const double*)s.tmp2);
+            KLAUNCH_CHECK(ctx);
+            bicg_xr_kernel<<<ew_grid_k(total), 256, 0, st>>>(total, m, x, r, p, sv, tv, s);
+            KLAUNCH_CHECK(ctx);
+            FEAST_TRY(launch_colnorm2(ctx, n, m, r, s.rn2));
+            kry_check_kernel<<<1, 128, 0, st>>>(m, s, tol2);
+            KLAUNCH_CHECK(ctx);
+            ++iters;
+            if (iters % check_every == 0 || iters == maxit) {
+                CUDA_TRY(ctx, cudaMemcpyAsync(&hf->nactive, s.nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(ctx, cudaMemcpyAsync(&hf->relmax, s.relmax, sizeof(double), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(ctx, cudaStreamSynchronize(st));
+                if (hf->nactive == 0) break;
+            }
+        }
+    }
+    if (out) {
+        out->iters = iters;
+        out->relres_max = hf->relmax;
+        out->converged = (hf->nactive == 0);
+    }
+    return 0;
+}

@@ -1,0 +1,403 @@
+"""Host-side mirror of the reference drivers over the C ABI.
+
+`feast`, `gen_feast`, `nlfeast` keep the names, argument order, keyword names,
+defaults, in-place mutation of X and return tuples of `feast!`, `gen_feast!`,
+`nlfeast!` (src/feast.jl:3-156, src/nlfeast.jl:2-84).  The outer loop below is
+the reference's loop with each inner block replaced by ONE call into
+libfeast_cuda.so; the m0 x m0 reduced eigenproblem / SVD stays on host LAPACK
+(scipy here, LinearAlgebra.eigen!/svd! in the Julia shim).
+
+There is no CPU fallback: every compute call goes through the CUDA library and
+raises FeastError when it is missing or no device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import scipy.linalg as sla
+import scipy.sparse as sp
+
+from . import _lib
+from ._lib import FeastError, FeastStats
+from .contour import (CircularContour, Contour, circular_contour_trapezoidal, in_contour)
+
+I = "I"  # stand-in for Julia's UniformScaling `I` as the B argument
+
+
+def _eig_sorted(Aq, Bq=None):
+    """eigen!(Aq) / eigen!(Aq, Bq) with Julia's (real, imag) ordering of the values."""
+    if Bq is None:
+        w, v = sla.eig(Aq, check_finite=False)
+    else:
+        w, v = sla.eig(Aq, Bq, check_finite=False)
+    p = np.lexsort((w.imag, w.real))
+    return np.ascontiguousarray(w[p]), np.asfortranarray(v[:, p])
+
+
+class FeastContext:
+    """Owns a feast_ctx*: device-resident operators, subspace blocks, stored factors."""
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        if device is None:
+            device = _default_device()
+        h = C.c_void_p()
+        _lib.check(self.lib.feast_ctx_create(C.byref(h), int(device)))
+        self.h = h
+        self.device = int(device)
+        self.n = 0
+        self.m0 = 0
+        self.nranks, self.rank = 1, 0
+        self.last_stats = None
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.feast_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc, allow=(0,)):
+        return _lib.check(rc, self.h, allow)
+
+    # -- operators
+    def set_operator(self, slot, M, n=None):
+        if M is None or (isinstance(M, str) and M == I):
+            self._ck(self.lib.feast_set_identity(self.h, slot, int(n)))
+            return
+        if sp.issparse(M):
+            M = sp.csc_matrix(M)
+            M.sort_indices()
+            if M.shape[0] != M.shape[1]:
+                raise ValueError("Incorrect dimensions of A, must be square")
+            is_c = np.iscomplexobj(M.data)
+            data = np.ascontiguousarray(M.data, dtype=np.complex128 if is_c else np.float64)
+            indptr = np.ascontiguousarray(M.indptr, dtype=np.int64)
+            indices = np.ascontiguousarray(M.indices, dtype=np.int64)
+            self._ck(self.lib.feast_set_csc(self.h, slot, M.shape[0], _lib.ptr(indptr), _lib.ptr(indices),
+                                            _lib.ptr(data), int(is_c), 0))
+            return
+        M = np.asarray(M)
+        if M.ndim != 2 or M.shape[0] != M.shape[1]:
+            raise ValueError("Incorrect dimensions of A, must be square")
+        is_c = np.iscomplexobj(M)
+        Mf = np.asfortranarray(M, dtype=np.complex128 if is_c else np.float64)  # also converts integer A
+        self._ck(self.lib.feast_set_dense(self.h, slot, Mf.shape[0], _lib.ptr(Mf), Mf.shape[0], int(is_c)))
+
+    def set_problem(self, kind, nslots, n):
+        self._ck(self.lib.feast_set_problem(self.h, kind, nslots))
+        self.n = n
+
+    def set_contour(self, nodes, weights):
+        z = np.ascontiguousarray(nodes, dtype=np.complex128)
+        w = np.ascontiguousarray(weights, dtype=np.complex128)
+        self._ck(self.lib.feast_set_contour(self.h, len(z), _lib.ptr(z), _lib.ptr(w)))
+
+    def set_solver(self, kind=_lib.SOLVER_AUTO, krylov=_lib.KRYLOV_AUTO, inner_tol=1e-8, max_inner=4000, store=False):
+        self._ck(self.lib.feast_set_solver(self.h, kind, krylov, float(inner_tol), int(max_inner), int(bool(store))))
+
+    def set_node_owners(self, owners):
+        o = np.ascontiguousarray(owners, dtype=np.int32)
+        self._ck(self.lib.feast_set_node_owners(self.h, len(o), _lib.ptr(o)))
+
+    def comm_init(self, nranks, rank, uid: bytes | None):
+        buf = (C.c_char * 128).from_buffer_copy(uid) if uid is not None else None
+        self._ck(self.lib.feast_comm_init(self.h, nranks, rank, buf))
+        self.nranks, self.rank = nranks, rank
+
+    # -- subspace
+    def set_subspace(self, X):
+        Xf = _lib.as_f_c128(X)
+        n, m0 = Xf.shape
+        self._ck(self.lib.feast_set_subspace(self.h, n, m0, _lib.ptr(Xf), n))
+        self.m0 = m0
+
+    def _get(self, fn):
+        out = np.empty((self.n, self.m0), dtype=np.complex128, order="F")
+        self._ck(fn(self.h, _lib.ptr(out), self.n))
+        return out
+
+    def get_X(self):
+        return self._get(self.lib.feast_get_X)
+
+    def get_Q(self):
+        return self._get(self.lib.feast_get_Q)
+
+    def get_R(self):
+        return self._get(self.lib.feast_get_R)
+
+    # -- phases
+    def project(self, generalized):
+        m = self.m0
+        Aq = np.empty((m, m), np.complex128, order="F")
+        Bq = np.empty((m, m), np.complex128, order="F") if generalized else None
+        self._ck(self.lib.feast_project(self.h, _lib.ptr(Aq), _lib.ptr(Bq)))
+        return Aq, Bq
+
+    def recover_residual(self, Xq, lam):
+        Xq = np.asfortranarray(Xq, dtype=np.complex128)
+        lam = np.ascontiguousarray(lam, dtype=np.complex128)
+        res = np.empty(self.m0, np.float64)
+        self._ck(self.lib.feast_recover_residual(self.h, _lib.ptr(Xq), _lib.ptr(lam), _lib.ptr(res)))
+        return res
+
+    def contour_apply(self, lam, first_pass=False):
+        st = FeastStats()
+        lam_p = None
+        if lam is not None:
+            lam = np.ascontiguousarray(lam, dtype=np.complex128)
+            lam_p = _lib.ptr(lam)
+        rc = self.lib.feast_contour_apply(self.h, lam_p, int(first_pass), C.byref(st))
+        self._ck(rc, allow=(0, _lib.FEAST_WARN_INNER_MAXIT))
+        self.last_stats = st.as_dict()
+        self.last_stats["warn_inner_maxit"] = rc == _lib.FEAST_WARN_INNER_MAXIT
+        return self.last_stats
+
+    def beyn_reduce(self):
+        m = self.m0
+        Rf = np.empty((m, m), np.complex128, order="F")
+        G1 = np.empty((m, m), np.complex128, order="F")
+        self._ck(self.lib.feast_beyn_reduce(self.h, _lib.ptr(Rf), _lib.ptr(G1)))
+        self._ck(self.lib.feast_sync(self.h))
+        return Rf, G1
+
+    def orthonormalize_X(self):
+        self._ck(self.lib.feast_orthonormalize_X(self.h))
+
+    # -- fine grained plugin path (factorizer / left_divider / finalize!)
+    def factorize(self, coefs):
+        cf = np.ascontiguousarray(coefs, dtype=np.complex128)
+        F = C.c_void_p()
+        self._ck(self.lib.feast_factorize(self.h, _lib.ptr(cf), len(cf), C.byref(F)))
+        return F
+
+    def solve(self, F, B, conj_transpose=False):
+        Bf = _lib.as_f_c128(B)
+        n, m = Bf.shape
+        Y = np.empty((n, m), np.complex128, order="F")
+        self._ck(self.lib.feast_solve(self.h, F, n, m, _lib.ptr(Bf), n, _lib.ptr(Y), n, int(conj_transpose)),
+                 allow=(0, _lib.FEAST_WARN_INNER_MAXIT))
+        self.m0 = m
+        return Y
+
+    def factor_free(self, F):
+        self.lib.feast_factor_free(self.h, F)
+
+    # -- kernel level
+    def apply_operator(self, slot, which=0, download=True, reps=0):
+        Y = np.empty((self.n, self.m0), np.complex128, order="F") if download else None
+        ms = C.c_float(0.0)
+        self._ck(self.lib.feast_apply_operator(self.h, slot, which, _lib.ptr(Y), self.n, int(reps),
+                                               C.byref(ms) if reps > 0 else None))
+        return Y, float(ms.value)
+
+    def sync(self):
+        self._ck(self.lib.feast_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.feast_launch_count(self.h))
+
+    def phase_times(self, reset=False):
+        t = np.zeros(3)
+        self._ck(self.lib.feast_phase_times(self.h, _lib.ptr(t), int(reset)))
+        return {"project_ms": t[0], "recover_ms": t[1], "contour_apply_ms": t[2]}
+
+
+def _default_device():
+    import os
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def _check_plugins(factorizer, left_divider, mixed_prec):
+    if factorizer is not None or left_divider is not None:
+        raise FeastError(-1, "custom factorizer/left_divider callbacks cannot run inside libfeast_cuda "
+                             "(no CPU fallback); use set_solver options instead")
+    if mixed_prec:
+        raise FeastError(-1, "mixed_prec=true is not implemented in this build (SURVEY 8f rank 2)")
+
+
+def _densify_if_mixed(A, B):
+    """The library needs all operators dense or all sparse (feast_set_problem)."""
+    if B is None or (isinstance(B, str)):
+        return A, B
+    if sp.issparse(A) != sp.issparse(B):
+        A = A.toarray() if sp.issparse(A) else A
+        B = B.toarray() if sp.issparse(B) else B
+    return A, B
+
+
+def iter_debug_print(nit, Lam, res, contour, spurious=1e-5):
+    """src/utils.jl:23-42"""
+    ins = in_contour(Lam, contour)
+    in_res = res[ins]
+    line = f"{nit}:\t{int(ins.sum())} ({int((in_res < spurious).sum())})\t"
+    if ins.sum() > 0:
+        line += f"{in_res.max()}"
+        conv = in_res[in_res < spurious]
+        if conv.size:
+            line += f"\t({conv.max()})"
+    print(line)
+
+
+def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, generalized, stats_out, comm):
+    N, m0 = X.shape
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("Incorrect dimensions of A, must be square")  # feast.jl:13
+    if A.shape[0] != N:
+        raise ValueError("Incorrect dimensions of X, must match A")  # feast.jl:15
+    own_ctx = ctx is None
+    if own_ctx:
+        ctx = FeastContext()
+    try:
+        A, B = _densify_if_mixed(A, B)
+        ctx.set_operator(0, A)
+        if generalized:
+            ctx.set_operator(1, B, n=N)
+            ctx.set_problem(_lib.PROBLEM_GENERALIZED, 2, N)
+        else:
+            ctx.set_problem(_lib.PROBLEM_STANDARD, 1, N)
+        if comm is not None:
+            comm(ctx)
+        ctx.set_contour(contour.nodes, contour.weights)
+        ctx.set_solver(store=store, **solver_opts)
+        ctx.set_subspace(X)
+        Lam = np.zeros(m0, complex)
+        res = np.zeros(m0)
+        hist = []
+        for nit in range(iter + 1):  # for nit=0:iter
+            Aq, Bq = ctx.project(generalized)  # feast.jl:41-43 / 117-121
+            Lam, Xq = _eig_sorted(Aq, Bq)  # feast.jl:45-47 / 122-124 (host LAPACK)
+            res = ctx.recover_residual(Xq, Lam)  # feast.jl:48-50 / 125-127
+            inside = in_contour(Lam, contour)
+            if debug:
+                iter_debug_print(nit, Lam, res, contour, 1e-5)
+            rec = {"nit": nit, "inside": int(inside.sum()),
+                   "max_res_inside": float(res[inside].max()) if inside.any() else float("nan")}
+            if inside.any() and res[inside].max() < eps:  # feast.jl:53
+                hist.append(rec)
+                if debug:
+                    print(f"converged in {nit} iteration")
+                break
+            if nit < iter:  # feast.jl:57
+                st = ctx.contour_apply(Lam)
+                rec.update(st)
+            hist.append(rec)
+        X[:, :] = ctx.get_X()
+        if stats_out is not None:
+            stats_out["history"] = hist
+            stats_out["Lam_all"] = Lam
+            stats_out["res_all"] = res
+            stats_out["launches"] = ctx.launch_count()
+            stats_out["phase_ms"] = ctx.phase_times()
+    finally:
+        if own_ctx:
+            ctx.close()
+    inside = in_contour(Lam, contour)
+    if not inside.any():
+        print("no eigenvalues found in contour!")  # feast.jl:78
+    return Lam[inside], X[:, inside], res[inside]
+
+
+def feast(X, A, contour: Contour | None = None, *, nodes=8, iter=10, c=complex(0.0, 0.0), r=1.0, eps=1e-12,
+          debug=False, store=False, mixed_prec=False, factorizer=None, left_divider=None,
+          ctx=None, solver_opts=None, stats=None, comm=None):
+    """feast!(X, A; ...) and feast!(X, A, contour; ...)  (src/feast.jl:3-80).
+
+    X (N x m0 complex128) is mutated in place and ends up holding all m0 unit-norm
+    Ritz vectors; returns (L[in], X[:, in], res[in]) filtered by in_contour.  `eps` is
+    the reference's keyword ϵ.
+    """
+    _check_plugins(factorizer, left_divider, mixed_prec)
+    if contour is None:
+        contour = circular_contour_trapezoidal(c, r, nodes)  # feast.jl:6
+    return _linear_driver(X, A, None, contour, iter, eps, debug, store, ctx, solver_opts or {}, False, stats, comm)
+
+
+def gen_feast(X, A, B, contour: Contour | None = None, *, nodes=8, iter=10, c=complex(0.0, 0.0), r=1.0,
+              debug=False, store=False, eps=1e-12, factorizer=None, left_divider=None,
+              ctx=None, solver_opts=None, stats=None, comm=None):
+    """gen_feast!(X, A, B; ...) and gen_feast!(X, A, B, contour; ...)  (src/feast.jl:82-156)."""
+    _check_plugins(factorizer, left_divider, False)
+    if contour is None:
+        contour = circular_contour_trapezoidal(c, r, nodes)  # feast.jl:85
+        store = False  # the reference's convenience wrapper drops `store` (feast.jl:86)
+    return _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts or {}, True, stats, comm)
+
+
+def nlfeast(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=10e-12, store=True,
+            spurious=1e-5, factorizer=None, left_divider=None, ctx=None, solver_opts=None, stats=None, comm=None):
+    """nlfeast!(T, X, nodes, iter; ...)  (src/nlfeast.jl:2-84) -> (L, X, res), all m0, unfiltered.
+
+    ADDED METHOD: `T` is the list of polynomial coefficient matrices
+    [A_0, ..., A_d] with T(z) = sum z^i A_i, so that assembly, solves and residuals run
+    on the device.  An opaque callable cannot be evaluated on the GPU and is rejected.
+    """
+    _check_plugins(factorizer, left_divider, False)
+    if callable(T):
+        raise TypeError("nlfeast on the B200 path needs polynomial coefficients [A_0, ..., A_d]; "
+                        "an opaque closure T(z) can only be evaluated on the host")
+    coeffs = list(T)
+    N, m0 = X.shape
+    if any(sp.issparse(a) for a in coeffs) and not all(sp.issparse(a) for a in coeffs):
+        coeffs = [a.toarray() if sp.issparse(a) else np.asarray(a) for a in coeffs]
+    own_ctx = ctx is None
+    if own_ctx:
+        ctx = FeastContext()
+    try:
+        for i, Ai in enumerate(coeffs):
+            ctx.set_operator(i, Ai, n=N)
+        ctx.set_problem(_lib.PROBLEM_POLYNOMIAL, len(coeffs), N)
+        if comm is not None:
+            comm(ctx)
+        contour = circular_contour_trapezoidal(c, r, nodes)  # nlfeast.jl:8 hard-wires circle + trapezoid
+        ctx.set_contour(contour.nodes, contour.weights)
+        ctx.set_solver(store=store, **(solver_opts or {}))
+        ctx.set_subspace(X)
+        ctx.orthonormalize_X()  # nlfeast.jl:12-13
+        Lam = np.zeros(m0, complex)
+        res = np.zeros(m0)
+        hist = []
+        for nit in range(iter + 1):
+            st = ctx.contour_apply(Lam if nit > 0 else None, first_pass=(nit == 0))  # nlfeast.jl:36-61
+            Rf, G1 = ctx.beyn_reduce()  # utils.jl:70-71 (tall part)
+            U, S, Vh = sla.svd(Rf, check_finite=False)  # m0 x m0 (host)
+            Am = (U.conj().T @ G1) @ Vh.conj().T * (1.0 / S)[None, :]  # utils.jl:71-73
+            w, v = sla.eig(Am, check_finite=False)  # utils.jl:74
+            p = np.lexsort((w.imag, w.real))
+            Lam = np.ascontiguousarray(w[p])
+            Xq = U @ v[:, p]  # utils.jl:75  X = U * vectors
+            res = ctx.recover_residual(Xq, Lam)  # nlfeast.jl:66-67
+            inside = in_contour(Lam, c, r)
+            res_inside = res[inside]
+            rec = {"nit": nit, "inside": int(inside.sum()),
+                   "max_res_inside": float(res_inside.max()) if inside.any() else float("nan")}
+            rec.update(st)
+            hist.append(rec)
+            if debug:
+                iter_debug_print(nit, Lam, res, CircularContour(c, r, contour.nodes, contour.weights), spurious)
+            if res_inside.size > 0 and res_inside.max() < eps:  # nlfeast.jl:73
+                break
+            good = res_inside[res_inside < spurious]
+            if nit > 1 and good.size > 0 and good.max() < eps:  # nlfeast.jl:76
+                break
+        X[:, :] = ctx.get_X()  # already unit-norm columns (normalize!, nlfeast.jl:82)
+        if stats is not None:
+            stats["history"] = hist
+            stats["launches"] = ctx.launch_count()
+            stats["phase_ms"] = ctx.phase_times()
+    finally:
+        if own_ctx:
+            ctx.close()
+    return Lam, X, res

@@ -1,0 +1,120 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol
+include/feast_cuda.h declares, its host-only entries (contour constructors) match
+the oracle, and compute entries fail loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import feast_oracle as fo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from feastsolver_jl_b200 import _lib, build
+    build.build()
+    return _lib.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    from feastsolver_jl_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "feast_cuda.h")).read()
+    declared = set(re.findall(r"FEAST_API[^;]*?\b(feast_\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.feast_version() == 100
+
+
+@pytest.mark.parametrize("N", [4, 8, 16, 32, 64])
+def test_contour_constructors_match_oracle(lib, N):
+    import feastsolver_jl_b200 as fs
+    pairs = [
+        (fs.circular_contour_trapezoidal(0.3 + 0.1j, 2.0, N), fo.circular_contour_trapezoidal(0.3 + 0.1j, 2.0, N)),
+        (fs.circular_contour_gauss(-1.0, 0.5, N), fo.circular_contour_gauss(-1.0, 0.5, N)),
+        (fs.rectangular_contour_gauss(-1 - 2j, 2 + 1j, N), fo.rectangular_contour_gauss(-1 - 2j, 2 + 1j, N)),
+        (fs.rectangular_contour_trapezoidal(-1 - 2j, 2 + 1j, N), fo.rectangular_contour_trapezoidal(-1 - 2j, 2 + 1j, N)),
+    ]
+    for a, b in pairs:
+        assert np.abs(a.nodes - b.nodes).max() <= 4e-15
+        assert np.abs(a.weights - b.weights).max() <= 1e-15
+
+
+def test_contour_errors(lib):
+    import feastsolver_jl_b200 as fs
+    with pytest.raises(ValueError, match="multiple of 2"):
+        fs.circular_contour_gauss(0, 1, 7)
+    with pytest.raises(ValueError, match="multiple of 4"):
+        fs.rectangular_contour_gauss(-1 - 1j, 1 + 1j, 6)
+    with pytest.raises(ValueError, match="multiple of 4"):
+        fs.rectangular_contour_trapezoidal(-1 - 1j, 1 + 1j, 10)
+    with pytest.raises(ValueError, match="Invalid corners"):
+        fs.rectangular_contour_trapezoidal(1 + 1j, -1 - 1j, 8)
+    ct = fs.circular_contour_trapezoidal(0.0, 1.0, 8)
+    assert fs.in_contour(np.array([1.0 + 0j]), ct)[0]
+    rc = fs.rectangular_contour_trapezoidal(-1 - 1j, 1 + 1j, 8)
+    assert not fs.in_contour(np.array([1.0 + 0j]), rc)[0]
+    assert abs(fs.rational_func(0.2, fs.circular_contour_trapezoidal(0.0, 1.0, 16)) - 1) < 1e-6
+    assert len(ct) == 1  # length(::Contour) = 1
+
+
+def test_gauss_legendre_matches_numpy(lib):
+    for n in (1, 2, 3, 8, 16, 33):
+        x = np.empty(n)
+        w = np.empty(n)
+        assert lib.feast_gauss_legendre(n, x.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p)) == 0
+        xr, wr = np.polynomial.legendre.leggauss(n)
+        assert np.abs(x - xr).max() < 2e-16 * 8 and np.abs(w - wr).max() < 1e-15
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the compute path must fail loudly, never fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import feastsolver_jl_b200 as fs
+    with pytest.raises(fs.FeastError, match="no CPU fallback"):
+        fs.FeastContext()
+    with pytest.raises(fs.FeastError):
+        fs.feast(np.ones((4, 2), complex), np.eye(4))
+
+
+def test_bad_arguments_return_negative_codes(lib):
+    assert lib.feast_ctx_create(None, 0) == -1
+    assert lib.feast_set_contour(None, 4, None, None) == -1
+    z = np.zeros(8, complex)
+    from feastsolver_jl_b200._lib import cplx
+    assert lib.feast_contour_circular_gauss(cplx(0), 1.0, 7, z.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p)) == -3
+    assert lib.feast_contour_rectangular_gauss(cplx(1 + 1j), cplx(0), 8, z.ctypes.data_as(C.c_void_p),
+                                               z.ctypes.data_as(C.c_void_p)) == -1
+    assert b"invalid" in lib.feast_last_error(None)
+
+
+def test_node_owner_partition():
+    import feastsolver_jl_b200 as fs
+    ct = fo.circular_contour_gauss(1.0, 0.5, 16)
+    for nr in (1, 2, 4, 8):
+        own = fs.node_owners(ct.nodes, nr)
+        counts = np.bincount(own, minlength=nr)
+        assert counts.max() - counts.min() == 0
+        from feastsolver_jl_b200.partition import node_cost
+        cost = node_cost(ct.nodes)
+        loads = np.array([cost[own == r].sum() for r in range(nr)])
+        assert loads.max() / loads.mean() < 1.35  # near/far nodes are paired
+
+
+def test_workload_generators():
+    from feastsolver_jl_b200 import workloads as wl
+    A, B = wl.laplacian3d_pencil(6)
+    assert A.shape == (216, 216) and A.nnz == 7 * 216 - 6 * 36
+    import scipy.linalg as sla
+    ex = np.sort(sla.eigh(A.toarray(), B.toarray(), eigvals_only=True))
+    an = wl.laplacian3d_spectrum(6)
+    assert np.abs(ex - an).max() < 1e-11
+    c, r, cnt = wl.c2_slice(6, target=10)
+    assert np.sum(np.abs(an - c) <= r) == cnt

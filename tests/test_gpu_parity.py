@@ -1,0 +1,340 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded inputs, against the committed golden fixtures, and at full size
+through size-independent properties (analytic spectra, linearity, residual bounds).
+
+Tolerances (BASELINE.json north_star): eigenvalues within 1e-10 relative, residuals
+within 10x the oracle's (with an absolute floor of a few ulps of ||A||), identical
+count of eigenvalues inside the contour.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import csc_unpack, x0
+from oracle import feast_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+EIG_RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def fs():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import feastsolver_jl_b200 as m
+    m.load_library()
+    return m
+
+
+def match_eigs(e_gpu, e_ref, rtol=EIG_RTOL, scale=None):
+    assert e_gpu.size == e_ref.size, (e_gpu.size, e_ref.size)
+    a, b = np.sort_complex(e_gpu), np.sort_complex(e_ref)
+    s = np.maximum(np.abs(b), 1.0) if scale is None else scale
+    # sort_complex can pair near-degenerate values differently: use nearest matching
+    for l in a:
+        assert (np.abs(b - l) / s).min() < rtol, (l, np.abs(b - l).min())
+
+
+def rm_block(ctx_get):
+    return np.asarray(ctx_get)
+
+
+# ------------------------------------------------------------------ kernel level
+@pytest.mark.parametrize("m0", [1, 5, 20, 64, 100])
+def test_spmm_matches_scipy(fs, m0):
+    rng = np.random.default_rng(m0)
+    n = 3000
+    S = sp.random(n, n, density=0.004, random_state=7, format="csc") + sp.identity(n, format="csc") * 0.5
+    S = S.tocsc()
+    X = x0(n, m0, 11)
+    with fs.FeastContext() as ctx:
+        ctx.set_operator(0, S)
+        ctx.set_problem(0, 1, n)
+        ctx.set_subspace(X)
+        Y, _ = ctx.apply_operator(0, which=0)
+    ref = S @ X
+    assert np.abs(Y - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_spmm_complex_values_and_ragged_rows(fs):
+    n = 777
+    rng = np.random.default_rng(3)
+    S = (sp.random(n, n, density=0.01, random_state=1) + 1j * sp.random(n, n, density=0.01, random_state=2)).tolil()
+    S[5, :] = 0  # empty row
+    S[6, :] = rng.standard_normal(n)  # dense row
+    S = S.tocsc()
+    X = x0(n, 33, 5)
+    with fs.FeastContext() as ctx:
+        ctx.set_operator(0, S)
+        ctx.set_problem(0, 1, n)
+        ctx.set_subspace(X)
+        Y, _ = ctx.apply_operator(0)
+    ref = S @ X
+    assert np.abs(Y - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert np.abs(Y[5]).max() == 0.0
+
+
+def test_spmm_linearity_full_size(fs):
+    """Size-independent property at a C2-like size: S(aX + bY) = aSX + bSY, and the 7-point
+    Laplacian applied to a separable sine mode returns lambda * mode."""
+    from feastsolver_jl_b200 import workloads as wl
+    m = 48
+    A, B = wl.laplacian3d_pencil(m)
+    n = m ** 3
+    th = np.arange(1, m + 1) * np.pi / (m + 1)
+    modes = []
+    lams = []
+    for (i, j, k) in [(1, 1, 1), (2, 1, 3), (5, 4, 2), (m, m, m)]:
+        v = np.einsum("a,b,c->abc", np.sin(i * th), np.sin(j * th), np.sin(k * th)).ravel()
+        modes.append(v)
+        lams.append(sum(2 - 2 * np.cos(q * np.pi / (m + 1)) for q in (i, j, k)))
+    X = np.array(modes).T.astype(complex) * (1 + 0.5j)
+    with fs.FeastContext() as ctx:
+        ctx.set_operator(0, A)
+        ctx.set_operator(1, B)
+        ctx.set_problem(1, 2, n)
+        ctx.set_subspace(X)
+        Y, _ = ctx.apply_operator(0)
+    for c in range(4):
+        assert np.abs(Y[:, c] - lams[c] * X[:, c]).max() < 1e-12 * lams[c]
+
+
+def test_dense_lu_solve_plugin_path(fs):
+    """factorizer / left_divider / finalize! seam (src/utils.jl:173-179) on a dense shifted matrix."""
+    rng = np.random.default_rng(0)
+    for n, nrhs in [(37, 3), (200, 20), (517, 64)]:
+        A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        z = 0.3 + 0.7j
+        Bm = x0(n, nrhs, 2)
+        with fs.FeastContext() as ctx:
+            ctx.set_operator(0, A)
+            ctx.set_problem(0, 1, n)
+            F = ctx.factorize([1.0, -z])  # A - z I
+            Y = ctx.solve(F, Bm)
+            Yh = ctx.solve(F, Bm, conj_transpose=True)
+            ctx.factor_free(F)
+        Z = A - z * np.eye(n)
+        ref = np.linalg.solve(Z, Bm)
+        refh = np.linalg.solve(Z.conj().T, Bm)
+        cond = np.linalg.cond(Z)
+        assert np.abs(Y - ref).max() <= 1e-14 * cond * np.abs(ref).max() + 1e-13
+        assert np.abs(Yh - refh).max() <= 1e-14 * cond * np.abs(refh).max() + 1e-13
+        assert np.abs(Z @ Y - Bm).max() <= 1e-12 * np.abs(Bm).max() * n
+
+
+def test_singular_matrix_reports_zero_pivot(fs):
+    A = np.zeros((8, 8))
+    A[0, 0] = 1.0
+    with fs.FeastContext() as ctx:
+        ctx.set_operator(0, A)
+        ctx.set_problem(0, 1, 8)
+        with pytest.raises(fs.FeastError) as ei:
+            ctx.factorize([1.0, 0.0])
+        assert ei.value.code == 1004
+
+
+# ------------------------------------------------------------------ reference assertions
+def test_T1_feast_diag(fs, linear_golden):  # test/runtests.jl:16-20
+    A = np.diag(np.arange(1, 26))  # integer dense A as upstream
+    X = linear_golden["T1_X0"].copy()
+    e, v, res = fs.feast(X, A, nodes=8, iter=10, c=1.5, r=2.0)
+    for t in (1, 2, 3):
+        assert np.isclose(e.real, t, rtol=1.5e-8, atol=0).any()
+    assert np.sort(res)[:3].max() < 1e-12
+    match_eigs(e, linear_golden["T1_e"])
+    assert v.shape == (25, e.size)
+    assert np.allclose(np.linalg.norm(X, axis=0), 1.0)  # X mutated in place: unit Ritz vectors
+
+
+def test_T2_gen_feast_diag(fs, linear_golden):  # test/runtests.jl:21-23
+    A = np.diag(np.arange(1, 26))
+    X = linear_golden["T2_X0"].copy()
+    e, v, res = fs.gen_feast(X, A, sp.diags(np.ones(25)), nodes=8, iter=100, c=1.5, r=2)
+    assert res.max() < 1e-12
+    match_eigs(e, linear_golden["T2_e"])
+
+
+@pytest.mark.parametrize("name", ["T3a", "T3b", "T3c", "T3d"])
+def test_T3_contours_sparse_laplacian(fs, linear_golden, name):  # test/runtests.jl:33-49
+    g = linear_golden
+    A = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(100, 100), format="csc")
+    C, R = 0.05 + 0j, 0.05
+    ct = {
+        "T3a": lambda: fs.circular_contour_trapezoidal(C, R, 8),
+        "T3b": lambda: fs.rectangular_contour_trapezoidal(0.0 - R * 1j, 2 * R + R * 1j, 8),
+        "T3c": lambda: fs.rectangular_contour_gauss(0.0 - R * 1j, 2 * R + R * 1j, 8),
+        "T3d": lambda: fs.circular_contour_gauss(C, R, 8),
+    }[name]()
+    assert np.abs(ct.nodes - g[name + "_nodes"]).max() < 1e-15
+    e, v, res = fs.feast(g[name + "_X0"].copy(), A, ct, eps=10e-15)
+    assert e.shape[0] == 10
+    assert res.max() < 10e-15
+    assert np.abs(np.sort(e.real) - g["lap1d_exact"]).max() < 1e-14
+    assert res.max() <= 10 * max(g[name + "_res"].max(), 4e-16)
+
+
+# ------------------------------------------------------------------ C1: dense Hermitian 500
+def test_C1_dense_hermitian_500(fs):
+    from feastsolver_jl_b200 import workloads as wl
+    A = wl.dense_hermitian(500, seed=7)
+    X0 = wl.rand_subspace(500, 20, seed=0)
+    ho, hg = [], {}
+    eo, vo, ro = fo.feast(X0.copy(), A, nodes=8, iter=10, c=0.0, r=0.55, eps=1e-12, history=ho)
+    Xg = X0.copy()
+    eg, vg, rg = fs.feast(Xg, A, nodes=8, iter=10, c=0.0, r=0.55, eps=1e-12, stats=hg)
+    exact = np.linalg.eigvalsh(A)
+    exact = exact[np.abs(exact) <= 0.55]
+    assert eg.size == eo.size == exact.size
+    match_eigs(eg, eo)
+    match_eigs(eg, exact.astype(complex))
+    assert rg.max() <= 10 * max(ro.max(), 1e-13)
+    assert len(hg["history"]) <= len(ho) + 1  # same outer iteration count (+-1)
+    # returned vectors are eigenvectors: subspace angle against the oracle's
+    Qo, _ = np.linalg.qr(vo)
+    assert np.linalg.norm(vg - Qo @ (Qo.conj().T @ vg)) < 1e-9
+
+
+def test_store_true_gives_same_answer(fs):
+    from feastsolver_jl_b200 import workloads as wl
+    A = wl.dense_hermitian(200, seed=3)
+    X0 = wl.rand_subspace(200, 12, seed=1)
+    ct = fs.circular_contour_trapezoidal(0.0, 0.8, 8)
+    e1, _, r1 = fs.feast(X0.copy(), A, ct, store=False)
+    e2, _, r2 = fs.feast(X0.copy(), A, ct, store=True)
+    match_eigs(e1, e2, rtol=1e-12)
+
+
+def test_dense_nonhermitian_rectangular(fs):
+    """test/contour_random.jl:8-21 shape: dense complex non-Hermitian 100x100, rectangle, 32 nodes."""
+    from feastsolver_jl_b200 import workloads as wl
+    A = wl.dense_nonhermitian(100, seed=1551) * np.sqrt(2)
+    R = 2.0
+    X0 = wl.rand_subspace(100, 20, seed=2)
+    cto = fo.rectangular_contour_trapezoidal(-R - 1j * R, R + R * 1j, 32)
+    ctg = fs.rectangular_contour_trapezoidal(-R - 1j * R, R + R * 1j, 32)
+    eo, vo, ro = fo.feast(X0.copy(), A, cto, eps=10e-14, iter=20)
+    eg, vg, rg = fs.feast(X0.copy(), A, ctg, eps=10e-14, iter=20)
+    ex = np.linalg.eigvals(A)
+    ex = ex[(np.abs(ex.real) < R) & (np.abs(ex.imag) < R)]
+    good_o = eo[ro < 1e-8]
+    good_g = eg[rg < 1e-8]
+    assert good_g.size == good_o.size
+    for l in good_g:
+        assert np.abs(ex - l).min() < 1e-9
+
+
+# ------------------------------------------------------------------ sparse generalized (C2 shape, reduced)
+@pytest.mark.parametrize("solver", ["dense_lu", "krylov"])
+def test_C2_reduced_sparse_generalized(fs, solver):
+    from feastsolver_jl_b200 import workloads as wl
+    from feastsolver_jl_b200 import _lib
+    m = 14
+    A, B = wl.laplacian3d_pencil(m)
+    n = m ** 3
+    c, r, cnt = wl.c2_slice(m, target=12)
+    X0 = wl.rand_subspace(n, 24, seed=0)
+    cto = fo.circular_contour_gauss(c, r, 16)
+    ctg = fs.circular_contour_gauss(c, r, 16)
+    eo, vo, ro = fo.gen_feast(X0.copy(), A, B, cto, eps=1e-12, iter=12)
+    opts = {"kind": _lib.SOLVER_DENSE_LU} if solver == "dense_lu" else {"kind": _lib.SOLVER_KRYLOV, "inner_tol": 1e-9}
+    st = {}
+    eg, vg, rg = fs.gen_feast(X0.copy(), A, B, ctg, eps=1e-12, iter=12, solver_opts=opts, stats=st)
+    exact = wl.laplacian3d_spectrum(m)
+    exact = exact[np.abs(exact - c) <= r]
+    assert eg.size == eo.size == cnt == exact.size
+    match_eigs(eg, eo)
+    match_eigs(eg, exact.astype(complex))
+    assert rg.max() <= 10 * max(ro.max(), 1e-13)
+    # residual definition check against scipy: || A v - l B v ||
+    Rchk = A @ vg - (B @ vg) * eg[None, :]
+    assert np.abs(np.linalg.norm(Rchk, axis=0) - rg).max() < 1e-12
+
+
+def test_generalized_nonsymmetric_sparse_bicgstab(fs):
+    """Non-symmetric sparse A exercises the BiCGStab inner solver."""
+    from feastsolver_jl_b200 import _lib
+    n = 400
+    rng = np.random.default_rng(5)
+    d = np.linspace(1.0, 40.0, n)
+    A = sp.diags([d, 0.3 * np.ones(n - 1), -0.2 * np.ones(n - 1)], [0, 1, -1], format="csc")
+    B = sp.diags([np.full(n, 2.0), 0.1 * np.ones(n - 1), 0.1 * np.ones(n - 1)], [0, 1, -1], format="csc")
+    ct_o = fo.circular_contour_trapezoidal(3.0, 1.0, 16)
+    ct_g = fs.circular_contour_trapezoidal(3.0, 1.0, 16)
+    X0 = x0(n, 16, 9)
+    eo, vo, ro = fo.gen_feast(X0.copy(), A, B, ct_o, iter=15)
+    eg, vg, rg = fs.gen_feast(X0.copy(), A, B, ct_g, iter=15,
+                              solver_opts={"kind": _lib.SOLVER_KRYLOV, "inner_tol": 1e-10, "max_inner": 2000})
+    match_eigs(eg, eo)
+    assert rg.max() <= 10 * max(ro.max(), 1e-12)
+
+
+# ------------------------------------------------------------------ nlfeast
+def test_nlfeast_butterfly_golden(fs, nep_fixtures, nlfeast_golden):
+    coeffs = [csc_unpack(nep_fixtures, f"butterfly{i}").toarray() for i in range(5)]
+    X = nlfeast_golden["butterfly_X0"].copy()
+    lam, X, res = fs.nlfeast(coeffs, X, 16, 30, c=1 + 1j, r=0.5, eps=1e-13)
+    inside = np.abs(lam - (1 + 1j)) <= 0.5
+    exact = nep_fixtures["butterfly_companion_inside"]
+    good = inside & (res < 1e-8)
+    assert good.sum() == 13 == exact.size
+    for l in lam[good]:
+        assert np.abs(exact - l).min() < 1e-10 * max(1.0, abs(l))
+    ores = nlfeast_golden["butterfly_nlfeast_res"]
+    olam = nlfeast_golden["butterfly_nlfeast_lam"]
+    oin = np.abs(olam - (1 + 1j)) <= 0.5
+    assert res[good].max() <= 10 * max(ores[oin].max(), 1e-13)
+    assert lam.size == 20 and X.shape == (64, 20)  # unfiltered return (nlfeast.jl:83)
+    assert np.allclose(np.linalg.norm(X, axis=0), 1.0)
+
+
+def test_nlfeast_sparse_butterfly_matches_dense(fs, nep_fixtures, nlfeast_golden):
+    """Same problem through the sparse union-pattern kernels (K9) instead of dense slots."""
+    coeffs = [csc_unpack(nep_fixtures, f"butterfly{i}") for i in range(5)]
+    X = nlfeast_golden["butterfly_X0"].copy()
+    lam, X, res = fs.nlfeast(coeffs, X, 16, 30, c=1 + 1j, r=0.5, eps=1e-13)
+    exact = nep_fixtures["butterfly_companion_inside"]
+    good = (np.abs(lam - (1 + 1j)) <= 0.5) & (res < 1e-8)
+    assert good.sum() == 13
+    for l in lam[good]:
+        assert np.abs(exact - l).min() < 1e-10 * max(1.0, abs(l))
+
+
+def test_nlfeast_linear_pencil_equals_feast(fs):
+    n = 100
+    A = np.diag(np.full(n, 2.0)) + np.diag(np.full(n - 1, -1.0), 1) + np.diag(np.full(n - 1, -1.0), -1)
+    lam, X, res = fs.nlfeast([-A, np.eye(n)], x0(n, 10, 5), 8, 10, c=0.02, r=0.02, eps=1e-12)
+    inside = np.abs(lam - 0.02) <= 0.02
+    exact = 2 - 2 * np.cos(np.arange(1, 7) * np.pi / 101)
+    exact = exact[np.abs(exact - 0.02) <= 0.02]
+    assert inside.sum() == exact.size
+    assert np.abs(np.sort(lam[inside].real) - exact).max() < 1e-12
+
+
+def test_system5_quadratic_count(fs, nep_fixtures):
+    """test/polynomial.jl problem: 50 eigenvalues in |l + 1.55| <= 0.05 (companion answer)."""
+    coeffs = [csc_unpack(nep_fixtures, f"system5_{i}") for i in range(3)]
+    exact = nep_fixtures["system5_companion_inside"]
+    lam, X, res = fs.nlfeast(coeffs, x0(1000, 80, 4), 32, 12, c=-1.55, r=0.05, eps=1e-12)
+    good = (np.abs(lam + 1.55) <= 0.05) & (res < 1e-8)
+    assert good.sum() == 50
+    for l in lam[good]:
+        assert np.abs(exact - l).min() < 1e-10 * abs(l)
+
+
+# ------------------------------------------------------------------ errors / edge cases
+def test_dimension_errors(fs):
+    with pytest.raises(ValueError, match="must be square"):
+        fs.feast(x0(4, 2, 0), np.ones((4, 3)))
+    with pytest.raises(ValueError, match="must match A"):
+        fs.feast(x0(5, 2, 0), np.eye(4))
+    with pytest.raises(fs.FeastError):
+        fs.feast(x0(4, 2, 0), np.eye(4), mixed_prec=True)
+
+
+def test_empty_contour_returns_empty(fs, capsys):
+    A = np.diag(np.arange(1.0, 11.0))
+    e, v, r = fs.feast(x0(10, 3, 0), A, nodes=8, iter=2, c=100.0, r=0.5)
+    assert e.size == 0 and v.shape == (10, 0) and r.size == 0
+    assert "no eigenvalues found in contour!" in capsys.readouterr().out  # feast.jl:78
