@@ -29,7 +29,8 @@ class c128(C.Structure):
 class FeastStats(C.Structure):
     _fields_ = [("nodes_local", C.c_int), ("inner_iters_total", C.c_int), ("inner_iters_max", C.c_int),
                 ("info", C.c_int), ("inner_relres_max", C.c_double), ("t_factor_ms", C.c_double),
-                ("t_solve_ms", C.c_double), ("t_reduce_ms", C.c_double), ("t_total_ms", C.c_double)]
+                ("t_solve_ms", C.c_double), ("t_reduce_ms", C.c_double), ("t_total_ms", C.c_double),
+                ("t_spmm_ms", C.c_double), ("spmm_launches", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -78,6 +79,8 @@ SIGNATURES = {
     "feast_factor_free": (_i, [_vp, _vp]),
     "feast_apply_operator": (_i, [_vp, _i, _i, _vp, _i64, _i, C.POINTER(C.c_float)]),
     "feast_sync": (_i, [_vp]),
+    "feast_timer_start": (_i, [_vp]),
+    "feast_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
     "feast_launch_count": (_i64, [_vp]),
     "feast_phase_times": (_i, [_vp, _vp, _i]),
 }

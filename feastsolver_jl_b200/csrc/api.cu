@@ -452,6 +452,8 @@ int feast_ctx_destroy(feast_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->sw0) cudaEventDestroy(ctx->sw0);
+    if (ctx->sw1) cudaEventDestroy(ctx->sw1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return 0;
@@ -835,6 +837,8 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
             st.inner_iters_total += kr.iters;
             st.inner_iters_max = std::max(st.inner_iters_max, kr.iters);
             st.inner_relres_max = std::max(st.inner_relres_max, kr.relres_max);
+            st.t_spmm_ms += kr.spmm_ms;
+            st.spmm_launches += kr.spmm_launches;
             if (!kr.converged) rc_final = FEAST_WARN_INNER_MAXIT;
         }
         // Q += (X - Y) diag(w/(z - l))  [feast.jl:68-70] ; polynomial: Q0, Q1 [nlfeast.jl:56-58]
@@ -1012,6 +1016,26 @@ int feast_sync(feast_ctx* ctx) {
     ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
     FEAST_TRY(bind_device(ctx));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int feast_timer_start(feast_ctx* ctx) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    FEAST_TRY(bind_device(ctx));
+    if (!ctx->sw0) { CUDA_TRY(ctx, cudaEventCreate(&ctx->sw0)); CUDA_TRY(ctx, cudaEventCreate(&ctx->sw1)); }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->sw0, ctx->stream));
+    return 0;
+}
+
+int feast_timer_stop(feast_ctx* ctx, float* ms) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, ms != nullptr, 2, "null output");
+    if (!ctx->sw0) return feast_fail(ctx, FEAST_ERR_STATE, "feast_timer_start has not been called");
+    FEAST_TRY(bind_device(ctx));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->sw1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->sw1));
+    CUDA_TRY(ctx, cudaEventElapsedTime(ms, ctx->sw0, ctx->sw1));
     return 0;
 }
 

@@ -143,6 +143,7 @@ struct feast_ctx {
 
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t sw0 = nullptr, sw1 = nullptr;   // user stopwatch (feast_timer_*)
     double phase_ms[3] = {0, 0, 0};
 };
 

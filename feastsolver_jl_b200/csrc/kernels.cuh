@@ -54,7 +54,7 @@ int launch_poly_fro_dense(feast_ctx* ctx, int64_t n, int m, int nslots, const c1
                           const c128* lam_d, double* fro2_d);
 
 // ---- krylov.cu ----------------------------------------------------------------
-struct KrylovResult { int iters; double relres_max; bool converged; };
+struct KrylovResult { int iters; double relres_max; bool converged; double spmm_ms; int spmm_launches; };
 // Solve Z Y = Rhs for all m columns with pseudo-block COCG (complex symmetric Z) or BiCGStab.
 // Z given by the union pattern + zvals.  Y, Rhs row-major n x m.  Y is overwritten (zero start).
 int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs, c128* Y,

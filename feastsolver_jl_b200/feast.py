@@ -21,6 +21,7 @@ import scipy.sparse as sp
 from . import _lib
 from ._lib import FeastError, FeastStats
 from .contour import (CircularContour, Contour, circular_contour_trapezoidal, in_contour)
+from .partition import node_owners
 
 I = "I"  # stand-in for Julia's UniformScaling `I` as the B argument
 
@@ -206,6 +207,14 @@ class FeastContext:
     def sync(self):
         self._ck(self.lib.feast_sync(self.h))
 
+    def timer_start(self):
+        self._ck(self.lib.feast_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0.0)
+        self._ck(self.lib.feast_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
     def launch_count(self):
         return int(self.lib.feast_launch_count(self.h))
 
@@ -271,6 +280,8 @@ def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, 
         if comm is not None:
             comm(ctx)
         ctx.set_contour(contour.nodes, contour.weights)
+        if ctx.nranks > 1:  # balanced node -> rank map (near-axis nodes cost more Krylov iterations)
+            ctx.set_node_owners(node_owners(contour.nodes, ctx.nranks))
         ctx.set_solver(store=store, **solver_opts)
         ctx.set_subspace(X)
         Lam = np.zeros(m0, complex)
@@ -363,6 +374,8 @@ def nlfeast(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=1
             comm(ctx)
         contour = circular_contour_trapezoidal(c, r, nodes)  # nlfeast.jl:8 hard-wires circle + trapezoid
         ctx.set_contour(contour.nodes, contour.weights)
+        if ctx.nranks > 1:
+            ctx.set_node_owners(node_owners(contour.nodes, ctx.nranks))
         ctx.set_solver(store=store, **(solver_opts or {}))
         ctx.set_subspace(X)
         ctx.orthonormalize_X()  # nlfeast.jl:12-13

@@ -75,6 +75,8 @@ typedef struct {
     double t_solve_ms;        /* device time in solves + fused accumulation         */
     double t_reduce_ms;       /* device time in the NCCL all-reduce                 */
     double t_total_ms;
+    double t_spmm_ms;         /* Krylov: device time inside the SpMM launches       */
+    int64_t spmm_launches;    /* Krylov: number of SpMM launches                    */
 } feast_stats;
 
 /* ---- library / context ---------------------------------------------- */
@@ -167,6 +169,11 @@ FEAST_API int  feast_factor_free(feast_ctx* ctx, feast_factor* F);
 FEAST_API int  feast_apply_operator(feast_ctx* ctx, int slot, int which, feast_c128* Y, int64_t ldy, int reps, float* ms);
 /* synchronise the library stream */
 FEAST_API int  feast_sync(feast_ctx* ctx);
+/* CUDA-event stopwatch on the library stream (the stream every kernel of this context is
+ * launched on): start records an event, stop records a second one, synchronises and returns
+ * the elapsed device-timeline milliseconds (host gaps between launches included).     */
+FEAST_API int  feast_timer_start(feast_ctx* ctx);
+FEAST_API int  feast_timer_stop(feast_ctx* ctx, float* ms);
 /* number of kernels this context has launched so far (bench.py gpu_launches) */
 FEAST_API int64_t feast_launch_count(const feast_ctx* ctx);
 /* device-timed phases since the last reset (ms): [0]=project [1]=recover [2]=contour_apply */

@@ -260,12 +260,13 @@ def test_generalized_nonsymmetric_sparse_bicgstab(fs):
     d = np.linspace(1.0, 40.0, n)
     A = sp.diags([d, 0.3 * np.ones(n - 1), -0.2 * np.ones(n - 1)], [0, 1, -1], format="csc")
     B = sp.diags([np.full(n, 2.0), 0.1 * np.ones(n - 1), 0.1 * np.ones(n - 1)], [0, 1, -1], format="csc")
-    ct_o = fo.circular_contour_trapezoidal(3.0, 1.0, 16)
-    ct_g = fs.circular_contour_trapezoidal(3.0, 1.0, 16)
-    X0 = x0(n, 16, 9)
-    eo, vo, ro = fo.gen_feast(X0.copy(), A, B, ct_o, iter=15)
-    eg, vg, rg = fs.gen_feast(X0.copy(), A, B, ct_g, iter=15,
+    ct_o = fo.circular_contour_trapezoidal(3.0, 0.3, 16)
+    ct_g = fs.circular_contour_trapezoidal(3.0, 0.3, 16)
+    X0 = x0(n, 24, 9)
+    eo, vo, ro = fo.gen_feast(X0.copy(), A, B, ct_o, iter=30)
+    eg, vg, rg = fs.gen_feast(X0.copy(), A, B, ct_g, iter=30,
                               solver_opts={"kind": _lib.SOLVER_KRYLOV, "inner_tol": 1e-10, "max_inner": 2000})
+    assert ro.max() < 1e-12  # the oracle itself converged, so the comparison is meaningful
     match_eigs(eg, eo)
     assert rg.max() <= 10 * max(ro.max(), 1e-12)
 
