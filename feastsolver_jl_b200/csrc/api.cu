@@ -3,6 +3,7 @@
 // fine-grained factorizer / left_divider plugin pair.  See include/feast_cuda.h for the
 // reference statements each entry replaces.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -41,6 +42,10 @@ int dev_alloc(feast_ctx* ctx, T** p, size_t count) {
         return feast_fail(ctx, e == cudaErrorMemoryAllocation ? FEAST_ERR_OOM : FEAST_ERR_CUDA,
                           "cudaMalloc of %zu bytes failed: %s", sizeof(T) * count, cudaGetErrorString(e));
     }
+    // FEAST_POISON=1 fills every allocation with 0xFF bytes (NaN doubles, negative ints) so
+    // that a read of uninitialised device memory shows up deterministically in the tests.
+    static const bool poison = getenv("FEAST_POISON") != nullptr;
+    if (poison) { cudaMemset(q, 0xFF, sizeof(T) * (count ? count : 1)); cudaDeviceSynchronize(); }
     *p = (T*)q;
     return 0;
 }
@@ -212,8 +217,11 @@ int build_union(feast_ctx* ctx) {
     for (int64_t i = 0; i <= n; ++i) rp32[i] = (int)rowptr[i];
     FEAST_TRY(dev_alloc(ctx, &ctx->u_rowptr, n + 1));
     FEAST_TRY(dev_alloc(ctx, &ctx->u_col, unnz));
-    CUDA_TRY(ctx, cudaMemcpy(ctx->u_rowptr, rp32.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice));
-    CUDA_TRY(ctx, cudaMemcpy(ctx->u_col, col.data(), sizeof(int) * unnz, cudaMemcpyHostToDevice));
+    // all uploads are ordered on the library stream: it is a NON-BLOCKING stream, so legacy-stream
+    // copies from pageable memory would not be ordered against the kernels launched on it
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->u_rowptr, rp32.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->u_col, col.data(), sizeof(int) * unnz, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     // pass 2: per-slot values on the union pattern
     bool all_sym = true;
     for (int s = 0; s < ctx->nslots; ++s) {
@@ -245,10 +253,12 @@ int build_union(feast_ctx* ctx) {
         op.is_complex = cplx;
         if (cplx) {
             FEAST_TRY(dev_alloc(ctx, &op.uvals_c, unnz));
-            CUDA_TRY(ctx, cudaMemcpy(op.uvals_c, cv.data(), sizeof(c128) * unnz, cudaMemcpyHostToDevice));
+            CUDA_TRY(ctx, cudaMemcpyAsync(op.uvals_c, cv.data(), sizeof(c128) * unnz, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         } else {
             FEAST_TRY(dev_alloc(ctx, &op.uvals_r, unnz));
-            CUDA_TRY(ctx, cudaMemcpy(op.uvals_r, rv.data(), sizeof(double) * unnz, cudaMemcpyHostToDevice));
+            CUDA_TRY(ctx, cudaMemcpyAsync(op.uvals_r, rv.data(), sizeof(double) * unnz, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         }
         // host copies are kept so that feast_set_problem can be called again (e.g. switching the
         // problem kind); an identity slot keeps its kind and additionally lives on the union pattern
@@ -474,11 +484,12 @@ int feast_set_dense(feast_ctx* ctx, int slot, int64_t n, const void* a, int64_t 
     Operator& op = ctx->ops[slot];
     FEAST_TRY(dev_alloc(ctx, &op.dense, (size_t)n * n));
     if (is_complex) {
-        CUDA_TRY(ctx, cudaMemcpy2D(op.dense, sizeof(c128) * n, a, sizeof(c128) * lda, sizeof(c128) * n, n, cudaMemcpyHostToDevice));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(op.dense, sizeof(c128) * n, a, sizeof(c128) * lda, sizeof(c128) * n, n, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     } else {
         double* tmp = nullptr;
         FEAST_TRY(dev_alloc(ctx, &tmp, (size_t)n * n));
-        cudaError_t e = cudaMemcpy2D(tmp, sizeof(double) * n, a, sizeof(double) * lda, sizeof(double) * n, n, cudaMemcpyHostToDevice);
+        cudaError_t e = cudaMemcpy2DAsync(tmp, sizeof(double) * n, a, sizeof(double) * lda, sizeof(double) * n, n, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) {
             int rc = launch_real_to_complex(ctx, n * n, tmp, op.dense);
             cudaStreamSynchronize(ctx->stream);
@@ -686,16 +697,22 @@ int feast_project(feast_ctx* ctx, feast_c128* Aq, feast_c128* Bq) {
     const int64_t n = ctx->n;
     const int m = ctx->m0;
     PhaseTimer tm(ctx, 0);
+    debug_check_finite(ctx, ctx->Q.p, 2 * n * m, "project: Q in");
     FEAST_TRY(orthonormalize(ctx, ctx->Q, nullptr));                       // feast.jl:41 / :117
+    debug_check_finite(ctx, ctx->Q.p, 2 * n * m, "project: Q orth");
     FEAST_TRY(ensure_block(ctx, ctx->W1));
     c128* G_d = ctx->small_d;
     FEAST_TRY(apply_slot(ctx, 0, ctx->Q.p, ctx->R.p));                     // R = A Q      feast.jl:42
+    debug_check_finite(ctx, ctx->R.p, 2 * n * m, "project: R = A Q");
     FEAST_TRY(launch_gram(ctx, n, m, ctx->Q.p, ctx->R.p, G_d));            // Aq = Q' R    feast.jl:43
+    debug_check_finite(ctx, G_d, 2 * m * m, "project: Aq");
     CUDA_TRY(ctx, cudaMemcpyAsync(Aq, G_d, sizeof(c128) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
     if (Bq) {
         c128* G2_d = ctx->small_d + (size_t)m * m;
         FEAST_TRY(apply_slot(ctx, 1, ctx->Q.p, ctx->W1.p));                // R = B Q      feast.jl:120
+        debug_check_finite(ctx, ctx->W1.p, 2 * n * m, "project: B Q");
         FEAST_TRY(launch_gram(ctx, n, m, ctx->Q.p, ctx->W1.p, G2_d));      // Bq = Q' R    feast.jl:121
+        debug_check_finite(ctx, G2_d, 2 * m * m, "project: Bq");
         CUDA_TRY(ctx, cudaMemcpyAsync(Bq, G2_d, sizeof(c128) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
     }
     tm.stop();
@@ -717,8 +734,10 @@ int feast_recover_residual(feast_ctx* ctx, const feast_c128* Xq, const feast_c12
     CUDA_TRY(ctx, cudaMemcpyAsync(M_d, Xq, sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(lam_d, lambda, sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
     FEAST_TRY(launch_update(ctx, n, m, ctx->Q.p, M_d, ctx->X.p));          // X = Q Xq            feast.jl:48
+    debug_check_finite(ctx, ctx->X.p, 2 * n * m, "recover: X = Q Xq");
     FEAST_TRY(launch_colnorm2(ctx, n, m, ctx->X.p, nrm_d));
     FEAST_TRY(launch_colnormalize(ctx, n, m, ctx->X.p, nrm_d));            // x_j /= ||x_j||      utils.jl:113
+    debug_check_finite(ctx, ctx->X.p, 2 * n * m, "recover: X normalised");
     double* hres = (double*)ctx->pinned;
     if (ctx->problem != FEAST_PROBLEM_POLYNOMIAL) {
         FEAST_TRY(apply_slot(ctx, 0, ctx->X.p, ctx->R.p));                 // R = A X
@@ -841,6 +860,8 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
             st.spmm_launches += kr.spmm_launches;
             if (!kr.converged) rc_final = FEAST_WARN_INNER_MAXIT;
         }
+        debug_check_finite(ctx, rhs, 2 * n * m, "contour: rhs");
+        debug_check_finite(ctx, ctx->W1.p, 2 * n * m, "contour: solve result");
         // Q += (X - Y) diag(w/(z - l))  [feast.jl:68-70] ; polynomial: Q0, Q1 [nlfeast.jl:56-58]
         FEAST_TRY(launch_accumulate(ctx, n, m, ctx->X.p, ctx->W1.p, d_d, ctx->Q.p, poly ? ctx->Q1.p : nullptr, z,
                                     first_pass != 0));

@@ -2,6 +2,7 @@
 // block update Y = X*M, column reductions, fused residual / accumulate epilogues, layout
 // conversion, dense assembly.  Replaces qr/mul!/rmul!/broadcast statements of
 // src/feast.jl:41-50,68-70,117-127 and src/utils.jl:111-116,166-171.
+#include <stdlib.h>
 #include "kernels.cuh"
 
 namespace {
@@ -429,5 +430,31 @@ int launch_poly_fro_dense(feast_ctx* ctx, int64_t n, int m, int nslots, const c1
     KLAUNCH_CHECK(ctx);
     reduce_partials2_kernel<<<ceil_div(m, 128), 128, 0, ctx->stream>>>(ctx->red_d, gx, m, fro2_d);
     KLAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------- diagnostics
+namespace {
+__global__ void count_nonfinite_kernel(int64_t count, const double* __restrict__ p, unsigned long long* out) {
+    unsigned long long c = 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x)
+        if (!isfinite(p[t])) ++c;
+    if (c) atomicAdd(out, c);
+}
+}  // namespace
+
+// FEAST_DEBUG_NAN=1: report blocks that contain non-finite entries (development aid)
+int debug_check_finite(feast_ctx* ctx, const void* p, int64_t ndoubles, const char* name) {
+    static const bool on = getenv("FEAST_DEBUG_NAN") != nullptr;
+    if (!on || !p) return 0;
+    unsigned long long* d = nullptr;
+    cudaMalloc(&d, sizeof(unsigned long long));
+    cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream);
+    count_nonfinite_kernel<<<kNumSMs, 256, 0, ctx->stream>>>(ndoubles, (const double*)p, d);
+    unsigned long long h = 0;
+    cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (h) fprintf(stderr, "[feast debug] %s: %llu non-finite of %lld doubles\n", name, h, (long long)ndoubles);
     return 0;
 }

@@ -69,3 +69,4 @@ int dense_getrs(feast_ctx* ctx, int64_t n, const c128* LU, const int* perm_d, in
                 bool conj_transpose);
 int dense_build_perm(feast_ctx* ctx, int64_t n, const int* ipiv_d, int* perm_d);
 size_t spmm_partials_bytes(int m);
+int debug_check_finite(feast_ctx* ctx, const void* p, int64_t ndoubles, const char* name);
