@@ -36,7 +36,7 @@ GRID = 100
 M0 = 64
 NODES = 16
 TARGET = 36
-INNER_TOL = 1e-6
+INNER_TOL = 1e-5
 MAX_INNER = 6000
 EPS = 1e-12
 CPU_GRID = 24          # reduced grid for the CPU arm (sparse LU of the 100^3 pencil does not fit)

@@ -86,6 +86,9 @@ void free_blocks(feast_ctx* ctx) {
     dev_free(ctx->stage);
     dev_free(ctx->small_d);
     dev_free(ctx->red_d);
+    dev_free(ctx->gm_V);
+    { char* g = (char*)ctx->gm_small; dev_free(g); ctx->gm_small = nullptr; }
+    ctx->gm_restart = 0;
     ctx->red_bytes = 0;
     ctx->m0 = 0;
 }
@@ -275,7 +278,7 @@ int effective_solver(const feast_ctx* ctx) {
 }
 int effective_krylov(const feast_ctx* ctx) {
     if (ctx->krylov != FEAST_KRYLOV_AUTO) return ctx->krylov;
-    return ctx->all_symmetric ? FEAST_KRYLOV_COCG : FEAST_KRYLOV_BICGSTAB;
+    return ctx->all_symmetric ? FEAST_KRYLOV_COCG : FEAST_KRYLOV_GMRES;
 }
 
 // Z = sum_i coef[i] * slot_i, assembled either dense (col-major n x n) or on the union pattern
@@ -311,6 +314,20 @@ void node_coefs(const feast_ctx* ctx, hc128 z, hc128* coef) {
 }
 
 int ensure_krylov_work(feast_ctx* ctx, int method) {
+    if (method == FEAST_KRYLOV_GMRES) {
+        if (ctx->gm_V) return 0;
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        const size_t blk = sizeof(c128) * (size_t)ctx->n * ctx->m0;
+        int64_t R = (int64_t)(0.6 * (double)free_b / (double)blk) - 1;   // basis gets at most 60 % of the free HBM
+        if (R > 400) R = 400;   // long recurrences are affordable in 180 GB of HBM and avoid restart stagnation
+        if (R > ctx->n) R = ctx->n;
+        if (R < 4) return feast_fail(ctx, FEAST_ERR_OOM, "not enough device memory for a GMRES basis");
+        ctx->gm_restart = (int)R;
+        FEAST_TRY(dev_alloc(ctx, &ctx->gm_V, (size_t)(R + 1) * ctx->n * ctx->m0));
+        FEAST_TRY(dev_alloc(ctx, (char**)&ctx->gm_small, gmres_small_bytes(ctx->m0, (int)R)));
+        return 0;
+    }
     FEAST_TRY(ensure_block(ctx, ctx->kr));
     FEAST_TRY(ensure_block(ctx, ctx->kp));
     FEAST_TRY(ensure_block(ctx, ctx->kq));
@@ -589,7 +606,7 @@ int feast_set_contour(feast_ctx* ctx, int nnodes, const feast_c128* z, const fea
 int feast_set_solver(feast_ctx* ctx, int kind, int krylov, double inner_tol, int max_inner, int store) {
     ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
     ARG_CHECK(ctx, kind >= 0 && kind <= 2, 2, "unknown solver kind");
-    ARG_CHECK(ctx, krylov >= 0 && krylov <= 2, 3, "unknown Krylov method");
+    ARG_CHECK(ctx, krylov >= 0 && krylov <= 3, 3, "unknown Krylov method");
     ARG_CHECK(ctx, inner_tol > 0 && inner_tol < 1, 4, "inner_tol must be in (0,1)");
     ARG_CHECK(ctx, max_inner >= 1, 5, "max_inner must be positive");
     ctx->solver = kind; ctx->krylov = krylov; ctx->inner_tol = inner_tol; ctx->max_inner = max_inner; ctx->store = store;
@@ -652,6 +669,7 @@ int feast_set_subspace(feast_ctx* ctx, int64_t n, int m0, const feast_c128* X, i
         // reduction scratch: split-K Gram partials (2*148 slices of m0 x m0) or SpMM/col-dot partials
         size_t red = std::max((size_t)2 * kNumSMs * m0 * m0 * sizeof(c128), spmm_partials_bytes(m0));
         red = std::max(red, (size_t)kNumSMs * 4 * 3 * (size_t)std::max(m0, 256) * sizeof(double));
+        red = std::max(red, (size_t)kNumSMs * 4 * 8 * 2 * (size_t)m0 * sizeof(double));   // GMRES multi-dot partials
         red = std::max(red, (size_t)1 << 20);
         FEAST_TRY(dev_alloc(ctx, &ctx->red_d, red / sizeof(double)));
         ctx->red_bytes = red;

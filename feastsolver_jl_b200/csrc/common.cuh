@@ -129,6 +129,9 @@ struct feast_ctx {
     int m0 = 0;
     BlockVec Q, X, R, Q1, W1, W2;       // Q1: second moment accumulator (polynomial)
     BlockVec kx, kr, kp, kq, ks, kt, kv, krh; // Krylov work
+    c128* gm_V = nullptr;         // GMRES basis: (gm_restart + 1) blocks
+    void* gm_small = nullptr;     // GMRES per-column Hessenberg / rotations
+    int gm_restart = 0;
     c128* stage = nullptr;        // n x m0 column-major staging (uploads / downloads)
     c128* small_d = nullptr;      // device scratch for m0 x m0 matrices (4 of them) + scalars
     double* red_d = nullptr;      // reduction partials

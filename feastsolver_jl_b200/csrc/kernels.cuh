@@ -60,6 +60,9 @@ struct KrylovResult { int iters; double relres_max; bool converged; double spmm_
 int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs, c128* Y,
                  double tol, int maxit, KrylovResult* out);
 
+int gmres_solve(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out);
+size_t gmres_small_bytes(int m, int R);
+
 // ---- dense.cu ------------------------------------------------------------------
 // In-place LU with partial pivoting of column-major n x n Z (zgetrf layout); ipiv device 0-based.
 int dense_getrf(feast_ctx* ctx, int64_t n, c128* Z, int* ipiv_d, int* info_out);

@@ -272,6 +272,7 @@ KryScal carve_scalars(feast_ctx* ctx) {
 
 int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit,
                  KrylovResult* out) {
+    if (method == FEAST_KRYLOV_GMRES) return gmres_solve(ctx, zvals, Rhs, Y, tol, maxit, out);
     const int64_t n = ctx->n;
     const int m = ctx->m0;
     const int64_t total = n * m;
@@ -387,6 +388,327 @@ int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs,
         out->iters = iters;
         out->relres_max = hf->relmax;
         out->converged = (hf->relmax <= tol * (1.0 + 1e-12));
+        out->spmm_ms = spmm_ms;
+        out->spmm_launches = spmm_launches;
+    }
+    return 0;
+}
+
+// =============================================================================== GMRES(R)
+// Pseudo-block restarted GMRES for general (non-symmetric) shifted operators: the m0 columns
+// share the SpMM and advance their own Arnoldi recurrences in lock step (per-column Hessenberg,
+// Givens rotations and residual estimates live on the device).  Orthogonalisation is classical
+// Gram-Schmidt applied twice (CGS2): all <v_i, w> of a step are one pass over the basis.
+namespace {
+
+constexpr int GM_NI = 8;  // basis vectors per dot-kernel pass
+
+struct GmSmall {          // device scalars; R = restart length, m = columns
+    c128* hraw;           // [(R+2)][m]   raw <v_i, w> (i<=k) and ||w|| at i=k+1 (real part)
+    c128* Hr;             // [m][R][R+1]  rotated (upper triangular) Hessenberg columns
+    double* cs;           // [m][R]
+    c128* sn;             // [m][R]
+    c128* g;              // [m][R+1]
+    c128* y;              // [R][m]
+    double* bn2;          // [m]
+    double* wn2;          // [m]
+    double* est;          // [m]  current residual estimate |g_{k+1}|
+    int* kdone;           // [m]  Arnoldi steps accepted for the column in this cycle
+    int* active;          // [m]
+    int* nactive;         // [1]
+    double* relmax;       // [1]
+};
+
+// partial dots of NI basis blocks against w: partials[block][NI][2m]
+__global__ void __launch_bounds__(256)
+gm_dots_kernel(int64_t n, int m, int ni, const c128* __restrict__ V, int64_t vstride, const c128* __restrict__ w,
+               double* __restrict__ partials) {
+    extern __shared__ double sm[];  // [256][2*GM_NI]
+    int cw = 1;
+    while (cw < m && cw < 256) cw <<= 1;
+    const int rpp = 256 / cw, cj = threadIdx.x % cw, rr = threadIdx.x / cw;
+    for (int jbase = 0; jbase < m; jbase += cw) {
+        const int j = jbase + cj;
+        double re[GM_NI], im[GM_NI];
+#pragma unroll
+        for (int i = 0; i < GM_NI; ++i) { re[i] = 0.0; im[i] = 0.0; }
+        if (j < m) {
+            for (int64_t r = (int64_t)blockIdx.x * rpp + rr; r < n; r += (int64_t)gridDim.x * rpp) {
+                const c128 y = __ldg(w + r * m + j);
+#pragma unroll
+                for (int i = 0; i < GM_NI; ++i) {
+                    if (i < ni) {
+                        const c128 x = __ldg(V + (int64_t)i * vstride + r * m + j);
+                        re[i] = fma(x.x, y.x, re[i]); re[i] = fma(x.y, y.y, re[i]);
+                        im[i] = fma(x.x, y.y, im[i]); im[i] = fma(-x.y, y.x, im[i]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < GM_NI; ++i) { sm[(2 * i) * 256 + threadIdx.x] = re[i]; sm[(2 * i + 1) * 256 + threadIdx.x] = im[i]; }
+        __syncthreads();
+        if (rr == 0 && j < m) {
+            for (int i = 0; i < ni; ++i) {
+                double a = 0.0, b = 0.0;
+                for (int k = 0; k < rpp; ++k) { a += sm[(2 * i) * 256 + k * cw + cj]; b += sm[(2 * i + 1) * 256 + k * cw + cj]; }
+                double* o = partials + ((int64_t)blockIdx.x * GM_NI + i) * 2 * m + 2 * j;
+                o[0] = a; o[1] = b;
+            }
+        }
+        __syncthreads();
+    }
+}
+// h[i0+i][j] (+)= sum_blocks partials
+__global__ void gm_dots_reduce_kernel(int nblocks, int m, int ni, const double* __restrict__ partials, c128* __restrict__ h,
+                                      int accumulate) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ni * m) return;
+    const int i = t / m, j = t % m;
+    double a = 0.0, b = 0.0;
+    for (int q = 0; q < nblocks; ++q) {
+        const double* o = partials + ((int64_t)q * GM_NI + i) * 2 * m + 2 * j;
+        a += o[0]; b += o[1];
+    }
+    c128 v = cmake(a, b);
+    if (accumulate) v = cadd(v, h[i * m + j]);
+    h[i * m + j] = v;
+}
+// w[:,j] -= sum_{i<nv} coef[i][j] V_i[:,j]   (sign = -1)   or   x[:,j] += sum ... (sign = +1)
+__global__ void __launch_bounds__(256)
+gm_axpy_kernel(int64_t total, int m, int nv, const c128* __restrict__ V, int64_t vstride, const c128* __restrict__ coef,
+               c128* __restrict__ w, double sign, const int* __restrict__ kdone) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % m);
+        const int lim = kdone ? kdone[j] : nv;
+        c128 acc = w[t];
+        for (int i = 0; i < nv && i < lim; ++i) {
+            const c128 c = __ldg(coef + i * m + j);
+            cfma(acc, cmake(sign * c.x, sign * c.y), __ldg(V + (int64_t)i * vstride + t));
+        }
+        w[t] = acc;
+    }
+}
+// v[:,j] = active_j ? w[:,j] / sqrt(wn2_j) : 0   (in place)
+__global__ void gm_normalize_kernel(int64_t total, int m, c128* __restrict__ w, const double* __restrict__ wn2,
+                                    const int* __restrict__ active) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % m);
+        const double q = wn2[j];
+        const double s = (active[j] && q > 0.0) ? 1.0 / sqrt(q) : 0.0;
+        const c128 v = w[t];
+        w[t] = cmake(v.x * s, v.y * s);
+    }
+}
+// start of a cycle: beta_j = sqrt(wn2_j); g = beta e1; flags
+__global__ void gm_cycle_init_kernel(int m, int R, GmSmall s, double tol, int first) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        if (first) s.bn2[j] = s.wn2[j];
+        const double beta = sqrt(s.wn2[j]);
+        const int act = (s.bn2[j] > 0.0 && beta > tol * sqrt(s.bn2[j])) ? 1 : 0;
+        s.active[j] = act;
+        s.kdone[j] = 0;
+        s.est[j] = beta;
+        for (int i = 0; i <= R; ++i) s.g[j * (R + 1) + i] = cmake(0.0, 0.0);
+        s.g[j * (R + 1)] = cmake(beta, 0.0);
+        if (act) atomicAdd(&cnt, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *s.nactive = cnt;
+}
+// after step k: h[0..k] = raw dots, wn2 = ||w||^2.  Apply old rotations, make the new one, update g.
+__global__ void gm_hessenberg_kernel(int m, int R, int k, GmSmall s, double tol) {
+    __shared__ int cnt;
+    __shared__ double rmax;
+    if (threadIdx.x == 0) { cnt = 0; rmax = 0.0; }
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        double rel = s.bn2[j] > 0.0 ? s.est[j] / sqrt(s.bn2[j]) : 0.0;
+        if (s.active[j]) {
+            c128* Hc = s.Hr + ((size_t)j * R + k) * (R + 1);
+            c128 hprev = s.hraw[0 * m + j];
+            for (int i = 0; i < k; ++i) {   // apply rotation i to (h_i, h_{i+1})
+                const c128 hnext = s.hraw[(i + 1) * m + j];
+                const double c = s.cs[j * R + i];
+                const c128 sn = s.sn[j * R + i];
+                const c128 a = cadd(cscale(c, hprev), cmul(sn, hnext));
+                const c128 b = cadd(cmul(cmake(-sn.x, sn.y), hprev), cscale(c, hnext));  // -conj(s) h_i + c h_{i+1}
+                Hc[i] = a;
+                hprev = b;
+            }
+            const c128 a = hprev;                       // rotated h_k
+            const double bnorm = sqrt(s.wn2[j]);        // h_{k+1,k} (real, >= 0)
+            const double an = sqrt(cabs2(a));
+            const double tt = sqrt(an * an + bnorm * bnorm);
+            double c = 1.0;
+            c128 sn = cmake(0.0, 0.0), rkk = a;
+            if (tt > 0.0) {
+                if (an > 0.0) {
+                    c = an / tt;
+                    const c128 ph = cscale(1.0 / an, a);      // a / |a|
+                    sn = cscale(bnorm / tt, ph);              // (a/|a|) conj(b)/t, b real
+                    rkk = cscale(tt, ph);
+                } else {
+                    c = 0.0; sn = cmake(1.0, 0.0); rkk = cmake(bnorm, 0.0);
+                }
+            }
+            Hc[k] = rkk;
+            s.cs[j * R + k] = c;
+            s.sn[j * R + k] = sn;
+            const c128 gk = s.g[j * (R + 1) + k];
+            s.g[j * (R + 1) + k] = cscale(c, gk);
+            const c128 gn = cmul(cmake(-sn.x, sn.y), gk);
+            s.g[j * (R + 1) + k + 1] = gn;
+            const double est = sqrt(cabs2(gn));
+            s.est[j] = est;
+            s.kdone[j] = k + 1;
+            rel = est / sqrt(s.bn2[j]);
+            if (!(est > tol * sqrt(s.bn2[j])) || !(bnorm > 0.0) || !isfinite(est)) s.active[j] = 0;  // converged / breakdown
+        }
+        if (s.active[j]) atomicAdd(&cnt, 1);
+        unsigned long long* addr = (unsigned long long*)&rmax;
+        unsigned long long old = *addr, assumed;
+        do {
+            assumed = old;
+            if (__longlong_as_double((long long)assumed) >= rel) break;
+            old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(rel));
+        } while (assumed != old);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *s.nactive = cnt; *s.relmax = rmax; }
+}
+// back substitution of the kdone_j x kdone_j triangle: y[i][j]
+__global__ void gm_solve_kernel(int m, int R, GmSmall s) {
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const int kd = s.kdone[j];
+        for (int i = kd - 1; i >= 0; --i) {
+            c128 acc = s.g[j * (R + 1) + i];
+            for (int q = i + 1; q < kd; ++q) {
+                const c128 h = s.Hr[((size_t)j * R + q) * (R + 1) + i];
+                cfma(acc, cmake(-h.x, -h.y), s.y[q * m + j]);
+            }
+            const c128 d = s.Hr[((size_t)j * R + i) * (R + 1) + i];
+            s.y[i * m + j] = cabs2(d) > 0.0 ? cdiv(acc, d) : cmake(0.0, 0.0);
+        }
+        for (int i = kd; i < R; ++i) s.y[i * m + j] = cmake(0.0, 0.0);
+    }
+}
+// a += b (small coefficient arrays)
+__global__ void gm_add_kernel(int count, c128* __restrict__ a, const c128* __restrict__ b) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < count) a[t] = cadd(a[t], b[t]);
+}
+// r = b - w
+__global__ void gm_residual_kernel(int64_t total, const c128* __restrict__ b, c128* __restrict__ w) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+        w[t] = csub(__ldg(b + t), w[t]);
+}
+
+}  // namespace
+
+size_t gmres_small_bytes(int m, int R) {
+    size_t c = (size_t)(R + 2) * m + (size_t)m * R * (R + 1) + (size_t)m * R + (size_t)m * (R + 1) + (size_t)R * m;  // c128
+    size_t d = (size_t)m * R + 3 * (size_t)m + 8;                                                                    // doubles
+    size_t i = 2 * (size_t)m + 8;                                                                                    // ints
+    return c * sizeof(c128) + d * sizeof(double) + i * sizeof(int) + 256;
+}
+
+int gmres_solve(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out) {
+    const int64_t n = ctx->n;
+    const int m = ctx->m0, R = ctx->gm_restart;
+    const int64_t total = n * m;
+    const size_t bytes = sizeof(c128) * total;
+    cudaStream_t st = ctx->stream;
+    c128* V = ctx->gm_V;
+    GmSmall s;
+    {
+        char* p = (char*)ctx->gm_small;
+        s.hraw = (c128*)p; p += sizeof(c128) * (size_t)(R + 2) * m;
+        s.Hr = (c128*)p;   p += sizeof(c128) * (size_t)m * R * (R + 1);
+        s.sn = (c128*)p;   p += sizeof(c128) * (size_t)m * R;
+        s.g = (c128*)p;    p += sizeof(c128) * (size_t)m * (R + 1);
+        s.y = (c128*)p;    p += sizeof(c128) * (size_t)R * m;
+        s.cs = (double*)p; p += sizeof(double) * (size_t)m * R;
+        s.bn2 = (double*)p; p += sizeof(double) * m;
+        s.wn2 = (double*)p; p += sizeof(double) * m;
+        s.est = (double*)p; p += sizeof(double) * m;
+        s.relmax = (double*)p; p += sizeof(double) * 8;
+        s.kdone = (int*)p; p += sizeof(int) * m;
+        s.active = (int*)p; p += sizeof(int) * m;
+        s.nactive = (int*)p;
+    }
+    struct HostFlag { int nactive; int pad; double relmax; };
+    HostFlag* hf = (HostFlag*)ctx->pinned;
+    hf->nactive = -1; hf->relmax = 1.0;
+    const int rgrid = red_grid_k(n, m);
+    const int egrid = ew_grid_k(total);
+    int iters = 0;
+    double spmm_ms = 0.0;
+    int spmm_launches = 0;
+    CUDA_TRY(ctx, cudaMemsetAsync(Y, 0, bytes, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(V, Rhs, bytes, cudaMemcpyDeviceToDevice, st));   // r0 = b (x0 = 0)
+    bool first = true, done = false;
+    while (!done && iters < maxit) {
+        FEAST_TRY(launch_colnorm2(ctx, n, m, V, s.wn2));
+        gm_cycle_init_kernel<<<1, 128, 0, st>>>(m, R, s, tol, first ? 1 : 0);
+        KLAUNCH_CHECK(ctx);
+        first = false;
+        gm_normalize_kernel<<<egrid, 256, 0, st>>>(total, m, V, s.wn2, s.active);
+        KLAUNCH_CHECK(ctx);
+        CUDA_TRY(ctx, cudaMemcpyAsync(&hf->nactive, s.nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (hf->nactive == 0) { done = true; break; }
+        int k = 0;
+        for (; k < R && iters < maxit; ++k) {
+            c128* w = V + (int64_t)(k + 1) * total;
+            FEAST_TRY(launch_spmm(ctx, n, m, ctx->u_rowptr, ctx->u_col, nullptr, zvals, V + (int64_t)k * total, m, w, m, nullptr));
+            ++spmm_launches;
+            for (int pass = 0; pass < 2; ++pass) {      // CGS2
+                for (int i0 = 0; i0 <= k; i0 += GM_NI) {
+                    const int ni = (k + 1 - i0) < GM_NI ? (k + 1 - i0) : GM_NI;
+                    gm_dots_kernel<<<rgrid, 256, sizeof(double) * 256 * 2 * GM_NI, st>>>(n, m, ni, V + (int64_t)i0 * total, total, w,
+                                                                                       ctx->red_d);
+                    KLAUNCH_CHECK(ctx);
+                    c128* hdst = (pass == 0 ? s.hraw : s.y) + (size_t)i0 * m;   // pass 1 corrections go to y (scratch)
+                    gm_dots_reduce_kernel<<<ceil_div(ni * m, 128), 128, 0, st>>>(rgrid, m, ni, ctx->red_d, hdst, 0);
+                    KLAUNCH_CHECK(ctx);
+                }
+                const c128* coef = (pass == 0 ? s.hraw : s.y);
+                gm_axpy_kernel<<<egrid, 256, 0, st>>>(total, m, k + 1, V, total, coef, w, -1.0, nullptr);
+                KLAUNCH_CHECK(ctx);
+            }
+            gm_add_kernel<<<ceil_div((k + 1) * m, 256), 256, 0, st>>>((k + 1) * m, s.hraw, s.y);   // h += h'
+            KLAUNCH_CHECK(ctx);
+            FEAST_TRY(launch_colnorm2(ctx, n, m, w, s.wn2));
+            gm_hessenberg_kernel<<<1, 128, 0, st>>>(m, R, k, s, tol);
+            KLAUNCH_CHECK(ctx);
+            gm_normalize_kernel<<<egrid, 256, 0, st>>>(total, m, w, s.wn2, s.active);
+            KLAUNCH_CHECK(ctx);
+            ++iters;
+            CUDA_TRY(ctx, cudaMemcpyAsync(&hf->nactive, s.nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaMemcpyAsync(&hf->relmax, s.relmax, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            if (hf->nactive == 0) { ++k; break; }
+        }
+        // x += V y
+        gm_solve_kernel<<<1, 128, 0, st>>>(m, R, s);
+        KLAUNCH_CHECK(ctx);
+        gm_axpy_kernel<<<egrid, 256, 0, st>>>(total, m, k, V, total, s.y, Y, 1.0, s.kdone);
+        KLAUNCH_CHECK(ctx);
+        if (hf->nactive == 0) { done = true; break; }
+        // restart: r = b - Z x
+        FEAST_TRY(launch_spmm(ctx, n, m, ctx->u_rowptr, ctx->u_col, nullptr, zvals, Y, m, V, m, nullptr));
+        ++spmm_launches;
+        gm_residual_kernel<<<egrid, 256, 0, st>>>(total, Rhs, V);
+        KLAUNCH_CHECK(ctx);
+    }
+    if (out) {
+        out->iters = iters;
+        out->relres_max = hf->relmax;
+        out->converged = done;
         out->spmm_ms = spmm_ms;
         out->spmm_launches = spmm_launches;
     }

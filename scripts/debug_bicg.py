@@ -10,7 +10,7 @@ d = np.linspace(1.0, 40.0, n)
 A = sp.diags([d, 0.3 * np.ones(n - 1), -0.2 * np.ones(n - 1)], [0, 1, -1], format="csc")
 B = sp.diags([np.full(n, 2.0), 0.1 * np.ones(n - 1), 0.1 * np.ones(n - 1)], [0, 1, -1], format="csc")
 ct = fs.circular_contour_trapezoidal(3.0, 0.3, 16)
-for kry in (_lib.KRYLOV_BICGSTAB,):
+for kry in (_lib.KRYLOV_GMRES, _lib.KRYLOV_BICGSTAB):
     ctx = fs.FeastContext()
     ctx.set_operator(0, A); ctx.set_operator(1, B); ctx.set_problem(1, 2, n)
     ctx.set_solver(kind=_lib.SOLVER_KRYLOV, krylov=kry, inner_tol=1e-10, max_inner=2000)
