@@ -73,7 +73,8 @@ void free_problem_derived(feast_ctx* ctx) {
     dev_free(ctx->zvals);
     dev_free(ctx->zdense);
     dev_free(ctx->zpiv);
-    for (auto& f : ctx->stored) { dev_free(f.lu); dev_free(f.ipiv); dev_free(f.perm); }
+    dev_free(ctx->zdinv);
+    for (auto& f : ctx->stored) { dev_free(f.lu); dev_free(f.ipiv); dev_free(f.perm); dev_free(f.dinv); }
     ctx->stored.clear();
     for (int i = 0; i < FEAST_MAX_SLOTS; ++i) { dev_free(ctx->ops[i].uvals_r); dev_free(ctx->ops[i].uvals_c); }
     ctx->problem_ready = false;
@@ -134,7 +135,7 @@ int apply_slot(feast_ctx* ctx, int slot, const c128* V, c128* W) {
         return 0;
     }
     if (op.kind == OP_DENSE)
-        return launch_zgemm(ctx, (int)n, m, n, hc128(1, 0), op.dense, 1, n, false, V, m, 1, hc128(0, 0), W, m, 1);
+        return launch_zgemm(ctx, (int)n, m, n, hc128(1, 0), op.dense, n, 1, false, V, m, 1, hc128(0, 0), W, m, 1);  // dense slots are row-major
     if (op.kind == OP_CSR)
         return launch_spmm(ctx, n, m, ctx->u_rowptr, ctx->u_col, op.uvals_r, op.uvals_c, V, m, W, m, nullptr);
     return feast_fail(ctx, FEAST_ERR_STATE, "operator slot %d is not set", slot);
@@ -346,9 +347,11 @@ int factor_dense(feast_ctx* ctx, const hc128* coef, DenseLU& f, int* info) {
     if (!f.lu) FEAST_TRY(dev_alloc(ctx, &f.lu, (size_t)n * n));
     if (!f.ipiv) FEAST_TRY(dev_alloc(ctx, &f.ipiv, n));
     if (!f.perm) FEAST_TRY(dev_alloc(ctx, &f.perm, n));
+    if (!f.dinv) FEAST_TRY(dev_alloc(ctx, &f.dinv, (size_t)2 * n * kDiagNB));
     FEAST_TRY(assemble_dense_Z(ctx, coef, f.lu));
     FEAST_TRY(dense_getrf(ctx, n, f.lu, f.ipiv, info));
     FEAST_TRY(dense_build_perm(ctx, n, f.ipiv, f.perm));
+    FEAST_TRY(dense_build_diag_inverses(ctx, n, f.lu, f.dinv));
     return 0;
 }
 
@@ -499,24 +502,24 @@ int feast_set_dense(feast_ctx* ctx, int slot, int64_t n, const void* a, int64_t 
     free_problem_derived(ctx);
     free_operator(ctx->ops[slot]);
     Operator& op = ctx->ops[slot];
+    // device storage of dense slots is ROW-major (see dense.cu): upload column-major, transpose once
     FEAST_TRY(dev_alloc(ctx, &op.dense, (size_t)n * n));
+    c128* cm = nullptr;
+    FEAST_TRY(dev_alloc(ctx, &cm, (size_t)n * n));
+    int rc = 0;
+    cudaError_t e;
     if (is_complex) {
-        CUDA_TRY(ctx, cudaMemcpy2DAsync(op.dense, sizeof(c128) * n, a, sizeof(c128) * lda, sizeof(c128) * n, n, cudaMemcpyHostToDevice, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        e = cudaMemcpy2DAsync(cm, sizeof(c128) * n, a, sizeof(c128) * lda, sizeof(c128) * n, n, cudaMemcpyHostToDevice, ctx->stream);
     } else {
-        double* tmp = nullptr;
-        FEAST_TRY(dev_alloc(ctx, &tmp, (size_t)n * n));
-        cudaError_t e = cudaMemcpy2DAsync(tmp, sizeof(double) * n, a, sizeof(double) * lda, sizeof(double) * n, n, cudaMemcpyHostToDevice, ctx->stream);
-        if (e == cudaSuccess) {
-            int rc = launch_real_to_complex(ctx, n * n, tmp, op.dense);
-            cudaStreamSynchronize(ctx->stream);
-            cudaFree(tmp);
-            if (rc) return rc;
-        } else {
-            cudaFree(tmp);
-            return feast_fail(ctx, FEAST_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
-        }
+        double* tmp = (double*)op.dense;   // reuse the destination as staging for the real upload
+        e = cudaMemcpy2DAsync(tmp, sizeof(double) * n, a, sizeof(double) * lda, sizeof(double) * n, n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) rc = launch_real_to_complex(ctx, n * n, tmp, cm);
     }
+    if (e == cudaSuccess && !rc) rc = launch_colmajor_to_rowmajor(ctx, n, (int)n, cm, n, op.dense);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(cm);
+    if (e != cudaSuccess) return feast_fail(ctx, FEAST_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    if (rc) return rc;
     op.kind = OP_DENSE; op.n = n; op.is_complex = true;
     return 0;
 }
@@ -598,7 +601,7 @@ int feast_set_contour(feast_ctx* ctx, int nnodes, const feast_c128* z, const fea
     // default owners: round-robin pairs node k with node k + nnodes/2 on the same rank when possible
     ctx->owner.assign(nnodes, 0);
     for (int k = 0; k < nnodes; ++k) ctx->owner[k] = k % ctx->nranks;
-    for (auto& f : ctx->stored) { dev_free(f.lu); dev_free(f.ipiv); dev_free(f.perm); }
+    for (auto& f : ctx->stored) { dev_free(f.lu); dev_free(f.ipiv); dev_free(f.perm); dev_free(f.dinv); }
     ctx->stored.clear();
     return 0;
 }
@@ -856,7 +859,8 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
             } else {
                 if (!ctx->zdense) FEAST_TRY(dev_alloc(ctx, &ctx->zdense, (size_t)n * n));
                 if (!ctx->zpiv) FEAST_TRY(dev_alloc(ctx, &ctx->zpiv, (size_t)2 * n));
-                scratch.lu = ctx->zdense; scratch.ipiv = ctx->zpiv; scratch.perm = ctx->zpiv + n;
+                if (!ctx->zdinv) FEAST_TRY(dev_alloc(ctx, &ctx->zdinv, (size_t)2 * n * kDiagNB));
+                scratch.lu = ctx->zdense; scratch.ipiv = ctx->zpiv; scratch.perm = ctx->zpiv + n; scratch.dinv = ctx->zdinv;
                 f = &scratch;
             }
             if (need_factor) {
@@ -865,7 +869,8 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
                 if (info && !st.info) st.info = info;
             }
             cudaEventRecord(e1, ctx->stream);
-            FEAST_TRY(dense_getrs(ctx, n, f->lu, f->perm, m, rhs, ctx->W1.p, false));         // ldiv!
+            FEAST_TRY(ensure_block(ctx, ctx->W2));
+            FEAST_TRY(dense_getrs(ctx, n, f->lu, f->perm, f->dinv, m, rhs, ctx->W1.p, false));         // ldiv!
         } else {
             FEAST_TRY(assemble_sparse_Z(ctx, coef, ctx->zvals));
             cudaEventRecord(e1, ctx->stream);
@@ -956,7 +961,7 @@ int feast_factorize(feast_ctx* ctx, const feast_c128* coef, int ncoef, feast_fac
         int rc = factor_dense(ctx, cf, F->lu, &info);
         if (rc) { delete F; return rc; }
         if (info) {
-            dev_free(F->lu.lu); dev_free(F->lu.ipiv); dev_free(F->lu.perm);
+            dev_free(F->lu.lu); dev_free(F->lu.ipiv); dev_free(F->lu.perm); dev_free(F->lu.dinv);
             delete F;
             return feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d", info);
         }
@@ -996,7 +1001,7 @@ int feast_solve(feast_ctx* ctx, const feast_factor* F, int64_t n, int nrhs, cons
     FEAST_TRY(launch_colmajor_to_rowmajor(ctx, n, m, ctx->stage, n, rhs));
     int rc_final = 0;
     if (F->kind == FEAST_SOLVER_DENSE_LU) {
-        FEAST_TRY(dense_getrs(ctx, n, F->lu.lu, F->lu.perm, m, rhs, ctx->W1.p, conj_transpose != 0));
+        FEAST_TRY(dense_getrs(ctx, n, F->lu.lu, F->lu.perm, F->lu.dinv, m, rhs, ctx->W1.p, conj_transpose != 0));
     } else {
         if (conj_transpose && !F->symmetric)
             return feast_fail(ctx, FEAST_ERR_STATE, "adjoint Krylov solve needs a symmetric operator in this build");
@@ -1020,7 +1025,7 @@ int feast_solve(feast_ctx* ctx, const feast_factor* F, int64_t n, int nrhs, cons
 int feast_factor_free(feast_ctx* ctx, feast_factor* F) {  // finalize!(F), src/utils.jl:173
     if (!F) return 0;
     if (ctx) cudaSetDevice(ctx->device);
-    dev_free(F->lu.lu); dev_free(F->lu.ipiv); dev_free(F->lu.perm);
+    dev_free(F->lu.lu); dev_free(F->lu.ipiv); dev_free(F->lu.perm); dev_free(F->lu.dinv);
     dev_free(F->zvals);
     delete F;
     return 0;

@@ -7,120 +7,6 @@
 
 namespace {
 
-// ============================================================================ generic ZGEMM
-// 64x64 output tile, K-chunk 16, 256 threads, 4x4 complex register tile per thread
-// (thread (ti,tj) owns rows ti+16a, cols tj+16b: conflict-free LDS.128).
-constexpr int TM = 64, TN = 64, TK = 16;
-
-struct GemmArgs {
-    int M, N;
-    int64_t K;
-    const c128* A; int64_t sAi, sAk; int conjA;
-    const c128* B; int64_t sBk, sBj;
-    c128* C; int64_t sCi, sCj;
-    c128 alpha, beta;
-    int64_t kchunk;   // K range per grid.z slice
-    c128* partial;    // split-K partial output [z][M*N] (column-major M x N) or nullptr
-};
-
-__global__ void __launch_bounds__(256, 2) zgemm_kernel(GemmArgs g) {
-    __shared__ c128 sA[TK][TM + 1];
-    __shared__ c128 sB[TK][TN + 1];
-    const int tid = threadIdx.x;
-    // consecutive threads walk the unit-stride dimension of C (coalesced epilogue)
-    const bool c_i_contig = (g.sCi == 1);
-    const int ti = c_i_contig ? (tid & 15) : (tid >> 4);
-    const int tj = c_i_contig ? (tid >> 4) : (tid & 15);
-    const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
-    const int64_t kbeg = (int64_t)blockIdx.z * g.kchunk;
-    int64_t kend = kbeg + g.kchunk;
-    if (kend > g.K) kend = g.K;
-
-    c128 acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = cmake(0.0, 0.0);
-
-    const bool a_k_contig = (g.sAk == 1);  // choose the coalesced loader
-    const bool b_j_contig = (g.sBj == 1);
-
-    for (int64_t k0 = kbeg; k0 < kend; k0 += TK) {
-        // ---- load A tile (TM x TK) ----
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            int ii, kk;
-            if (a_k_contig) { kk = tid & 15; ii = (tid >> 4) + 16 * r; }
-            else            { ii = tid & 63; kk = (tid >> 6) + 4 * r; }
-            const int gi = i0 + ii;
-            const int64_t gk = k0 + kk;
-            c128 v = cmake(0.0, 0.0);
-            if (gi < g.M && gk < kend) {
-                v = g.A[gi * g.sAi + gk * g.sAk];
-                if (g.conjA) v.y = -v.y;
-            }
-            sA[kk][ii] = v;
-        }
-        // ---- load B tile (TK x TN) ----
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            int jj, kk;
-            if (b_j_contig) { jj = tid & 63; kk = (tid >> 6) + 4 * r; }
-            else            { kk = tid & 15; jj = (tid >> 4) + 16 * r; }
-            const int gj = j0 + jj;
-            const int64_t gk = k0 + kk;
-            c128 v = cmake(0.0, 0.0);
-            if (gj < g.N && gk < kend) v = g.B[gk * g.sBk + gj * g.sBj];
-            sB[kk][jj] = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < TK; ++kk) {
-            c128 av[4], bv[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) av[a] = sA[kk][ti + 16 * a];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) bv[b] = sB[kk][tj + 16 * b];
-#pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) cfma(acc[a][b], av[a], bv[b]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int gi = i0 + ti + 16 * a;
-        if (gi >= g.M) continue;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int gj = j0 + tj + 16 * b;
-            if (gj >= g.N) continue;
-            if (g.partial) {
-                g.partial[(int64_t)blockIdx.z * g.M * g.N + (int64_t)gj * g.M + gi] = acc[a][b];
-            } else {
-                c128 r = cmul(g.alpha, acc[a][b]);
-                c128* cp = g.C + gi * g.sCi + gj * g.sCj;
-                if (g.beta.x != 0.0 || g.beta.y != 0.0) r = cadd(r, cmul(g.beta, *cp));
-                *cp = r;
-            }
-        }
-    }
-}
-
-__global__ void splitk_reduce_kernel(const c128* __restrict__ partial, int nz, int M, int N, c128 alpha,
-                                     c128* __restrict__ C, int64_t sCi, int64_t sCj) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= M * N) return;
-    double re = 0.0, im = 0.0;
-    for (int z = 0; z < nz; ++z) {
-        c128 v = partial[(int64_t)z * M * N + t];
-        re += v.x; im += v.y;
-    }
-    const int i = t % M, j = t / M;
-    C[i * sCi + j * sCj] = cmul(alpha, cmake(re, im));
-}
-
 // ============================================================================ column reductions
 // block = 256 threads laid out as (rows_per_pass = 256/GW) x GW lanes over columns
 template <bool CONJ, bool NORM>
@@ -286,46 +172,6 @@ int ew_grid(int64_t total) {
 }  // namespace
 
 // ------------------------------------------------------------------------------- launchers
-int launch_zgemm(feast_ctx* ctx, int M, int N, int64_t K, hc128 alpha, const c128* A, int64_t sAi, int64_t sAk,
-                 bool conjA, const c128* B, int64_t sBk, int64_t sBj, hc128 beta, c128* C, int64_t sCi, int64_t sCj) {
-    if (M <= 0 || N <= 0) return 0;
-    GemmArgs g;
-    g.M = M; g.N = N; g.K = K;
-    g.A = A; g.sAi = sAi; g.sAk = sAk; g.conjA = conjA ? 1 : 0;
-    g.B = B; g.sBk = sBk; g.sBj = sBj;
-    g.C = C; g.sCi = sCi; g.sCj = sCj;
-    g.alpha = cmake(alpha.real(), alpha.imag());
-    g.beta = cmake(beta.real(), beta.imag());
-    const int gx = ceil_div(M, TM), gy = ceil_div(N, TN);
-    int splitk = 1;
-    const bool beta_zero = (beta == hc128(0.0, 0.0));
-    if (beta_zero && (int64_t)gx * gy < kNumSMs && K >= 4096) {  // tall-skinny: split K over the SMs
-        splitk = (2 * kNumSMs) / (gx * gy);
-        int64_t maxsplit = K / 512;
-        if (splitk > maxsplit) splitk = (int)maxsplit;
-        if (splitk < 1) splitk = 1;
-        while (splitk > 1 && (size_t)splitk * M * N * sizeof(c128) > ctx->red_bytes) --splitk;
-    }
-    if (splitk > 1) {
-        int64_t kc = (K + splitk - 1) / splitk;
-        kc = ((kc + TK - 1) / TK) * TK;
-        splitk = (int)((K + kc - 1) / kc);
-        g.kchunk = kc;
-        g.partial = (c128*)ctx->red_d;
-        zgemm_kernel<<<dim3(gx, gy, splitk), 256, 0, ctx->stream>>>(g);
-        KLAUNCH_CHECK(ctx);
-        splitk_reduce_kernel<<<ceil_div((int64_t)M * N, 256), 256, 0, ctx->stream>>>(g.partial, splitk, M, N, g.alpha,
-                                                                                  C, sCi, sCj);
-        KLAUNCH_CHECK(ctx);
-    } else {
-        g.kchunk = K > 0 ? K : 1;
-        g.partial = nullptr;
-        zgemm_kernel<<<dim3(gx, gy, 1), 256, 0, ctx->stream>>>(g);
-        KLAUNCH_CHECK(ctx);
-    }
-    return 0;
-}
-
 int launch_gram(feast_ctx* ctx, int64_t n, int m, const c128* A, const c128* B, c128* G_d) {
     // G(i,j) = sum_k conj(A[k,i]) B[k,j];  A(i,k) := A_rm[k*m + i]
     return launch_zgemm(ctx, m, m, n, hc128(1, 0), A, 1, m, true, B, m, 1, hc128(0, 0), G_d, 1, m);

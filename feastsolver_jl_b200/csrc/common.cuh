@@ -79,6 +79,7 @@ struct DenseLU {             // one stored factorisation (column-major, LAPACK g
     c128* lu = nullptr;
     int*  ipiv = nullptr;    // device, 0-based absolute row indices (LAPACK interchange sequence)
     int*  perm = nullptr;    // device, perm[i] = source row of permuted row i
+    c128* dinv = nullptr;    // explicit inverses of the diagonal blocks of L then U (2 x n x kDiagNB, row-major blocks)
     int64_t n = 0;
 };
 
@@ -112,6 +113,7 @@ struct feast_ctx {
     c128* zvals = nullptr;        // assembled shifted operator on the union pattern
     c128* zdense = nullptr;       // assembled dense shifted operator (n x n col-major)
     int*  zpiv = nullptr;
+    c128* zdinv = nullptr;        // diagonal-block inverses of the scratch factorisation
 
     // contour
     std::vector<hc128> znodes, zweights;
@@ -123,6 +125,7 @@ struct feast_ctx {
     int store = 0;
     std::vector<DenseLU> stored;  // per node (only local nodes populated)
     bool panel_attr_set = false;
+    bool dmma_attr_set = false;
     int dense_threshold = 6000;   // sparse problems up to this n are solved by dense LU
 
     // subspace blocks
@@ -180,4 +183,5 @@ int feast_fail(feast_ctx* ctx, int code, const char* fmt, ...);
     } while (0)
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+constexpr int kDiagNB = 256;   // diagonal-block size of the blocked triangular solves (dense.cu)
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this

@@ -1,4 +1,6 @@
 // K2 / K3: dense complex128 LU with partial pivoting (recursive, GEMM-rich) and the
+// [storage: the factored matrix is ROW-MAJOR, Z(i,j) = Z[i*ld + j], so that row interchanges move
+//  contiguous segments (the column-major laswp was 30 % of the LU time in the first ncu launch list)]
 // multi-right-hand-side triangular solves.  Replaces `factorizer(C)` = lu and
 // `left_divider(temp, F, R)` = ldiv! of src/utils.jl:175-179 / src/feast.jl:30,36,62,65
 // (LAPACK zgetrf / zgetrs upstream).  Same pivoting rule as zgetf2: the pivot is the
@@ -49,8 +51,8 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(PanelArgs a) {
     if (nr > R) nr = R;
     if (nr < 0) nr = 0;
     for (int idx = tid; idx < nr * w; idx += 256) {
-        const int r = idx % nr, k = idx / nr;
-        slab[k * R + r] = a.A[(int64_t)k * a.lda + r0 + r];
+        const int k = idx % w, r = idx / w;     // consecutive threads read consecutive columns of a row
+        slab[k * R + r] = a.A[(int64_t)(r0 + r) * a.lda + k];
     }
     __syncthreads();
     for (int jj = 0; jj < w; ++jj) {
@@ -136,20 +138,27 @@ __global__ void __launch_bounds__(256) lu_panel_kernel(PanelArgs a) {
         __syncthreads();
     }
     for (int idx = tid; idx < nr * w; idx += 256) {
-        const int r = idx % nr, k = idx / nr;
-        a.A[(int64_t)k * a.lda + r0 + r] = slab[k * R + r];
+        const int k = idx % w, r = idx / w;
+        a.A[(int64_t)(r0 + r) * a.lda + k] = slab[k * R + r];
     }
 }
 
-// apply row interchanges ipiv[k0..k1) to columns [c0, c0+nc) of column-major A
-__global__ void laswp_kernel(c128* __restrict__ A, int64_t lda, int c0, int nc, const int* __restrict__ ipiv, int k0,
-                             int k1) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nc) return;
-    c128* colp = A + (int64_t)(c0 + c) * lda;
+// Apply the row interchanges ipiv[k0..k1) of ONE panel to every column outside the panel
+// (columns [0, k0) and [k1, n)) of ROW-major A, right after the panel is factored (the LAPACK
+// right-looking convention).  Consecutive threads own consecutive columns, so each interchange moves
+// contiguous row segments, and a thread's sequential chain is only the panel width (<= 32) long.
+__global__ void laswp_kernel(c128* __restrict__ A, int64_t lda, int n, const int* __restrict__ ipiv, int k0, int k1) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n - (k1 - k0)) return;
+    if (c >= k0) c += (k1 - k0);          // skip the panel's own columns
+    c128* colp = A + c;
     for (int k = k0; k < k1; ++k) {
         const int p = ipiv[k];
-        if (p != k) { const c128 t = colp[k]; colp[k] = colp[p]; colp[p] = t; }
+        if (p != k) {
+            const c128 t = colp[(int64_t)k * lda];
+            colp[(int64_t)k * lda] = colp[(int64_t)p * lda];
+            colp[(int64_t)p * lda] = t;
+        }
     }
 }
 
@@ -267,7 +276,7 @@ int trsm_rec(feast_ctx* ctx, int h, int ncols, const c128* T, int64_t sTi, int64
 
 int lu_panel(feast_ctx* ctx, int64_t n, c128* Z, int64_t lda, int j0, int w, int* ipiv, LUWork& wk) {
     PanelArgs a;
-    a.A = Z + (int64_t)j0 * lda + j0;
+    a.A = Z + (int64_t)j0 * lda + j0;   // row-major: (row j0, col j0)
     a.lda = lda;
     a.rows = (int)(n - j0);
     a.w = w;
@@ -291,6 +300,10 @@ int lu_panel(feast_ctx* ctx, int64_t n, c128* Z, int64_t lda, int j0, int w, int
     void* args[] = {&a};
     CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(G), dim3(256), args, smem, ctx->stream));
     ctx->launches++;
+    if (n > w) {
+        laswp_kernel<<<ceil_div(n - w, 256), 256, 0, ctx->stream>>>(Z, lda, (int)n, ipiv, j0, j0 + w);
+        KLAUNCH_CHECK(ctx);
+    }
     return 0;
 }
 
@@ -300,20 +313,15 @@ int lu_rec(feast_ctx* ctx, int64_t n, c128* Z, int64_t lda, int j0, int w, int* 
     if (h >= w) h = w - 32;
     const int w2 = w - h;
     FEAST_TRY(lu_rec(ctx, n, Z, lda, j0, h, ipiv, wk));
-    // right part: swaps, U12 = L11^-1 A12, A22 -= L21 U12
-    laswp_kernel<<<ceil_div(w2, 128), 128, 0, ctx->stream>>>(Z, lda, j0 + h, w2, ipiv, j0, j0 + h);
-    KLAUNCH_CHECK(ctx);
-    c128* A11 = Z + (int64_t)j0 * lda + j0;
-    c128* A12 = Z + (int64_t)(j0 + h) * lda + j0;
-    c128* A21 = A11 + h;
-    c128* A22 = A12 + h;
-    FEAST_TRY((trsm_rec<true, true>(ctx, h, w2, A11, 1, lda, false, A12, 1, lda)));
+    // right part (its rows were already interchanged panel by panel): U12 = L11^-1 A12, A22 -= L21 U12
+    c128* A11 = Z + (int64_t)j0 * lda + j0;          // row-major blocks
+    c128* A12 = A11 + h;
+    c128* A21 = Z + (int64_t)(j0 + h) * lda + j0;
+    c128* A22 = A21 + h;
+    FEAST_TRY((trsm_rec<true, true>(ctx, h, w2, A11, lda, 1, false, A12, lda, 1)));
     const int mrows = (int)(n - j0 - h);
-    FEAST_TRY(launch_zgemm(ctx, mrows, w2, h, hc128(-1, 0), A21, 1, lda, false, A12, 1, lda, hc128(1, 0), A22, 1, lda));
+    FEAST_TRY(launch_zgemm(ctx, mrows, w2, h, hc128(-1, 0), A21, lda, 1, false, A12, lda, 1, hc128(1, 0), A22, lda, 1));
     FEAST_TRY(lu_rec(ctx, n, Z, lda, j0 + h, w2, ipiv, wk));
-    // left part: apply the right half's interchanges
-    laswp_kernel<<<ceil_div(h, 128), 128, 0, ctx->stream>>>(Z, lda, j0, h, ipiv, j0 + h, j0 + w);
-    KLAUNCH_CHECK(ctx);
     return 0;
 }
 
@@ -345,8 +353,47 @@ int dense_build_perm(feast_ctx* ctx, int64_t n, const int* ipiv_d, int* perm_d) 
     return 0;
 }
 
-int dense_getrs(feast_ctx* ctx, int64_t n, const c128* LU, const int* perm_d, int m, const c128* Rhs, c128* Y,
-                bool conj_transpose) {
+namespace {
+__global__ void set_identity_blocks_kernel(int64_t n, int nb, c128* __restrict__ D) {
+    // D is n x nb (row-major); block k = rows [k*nb, (k+1)*nb): identity on its own diagonal
+    const int64_t total = n * nb;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / nb;
+        const int j = (int)(t % nb);
+        D[t] = ((int)(i % nb) == j) ? cmake(1.0, 0.0) : cmake(0.0, 0.0);
+    }
+}
+}  // namespace
+
+// Explicit inverses of the kDiagNB x kDiagNB diagonal blocks of L (unit lower) and U (upper), computed
+// once per factorisation with the recursive TRSM on an identity right-hand side.  They turn every
+// diagonal step of the triangular solves into one DMMA GEMM (the recursive solve was launch-bound:
+// ~2000 tiny kernels per node solve at n = 16384).
+int dense_build_diag_inverses(feast_ctx* ctx, int64_t n, const c128* LU, c128* dinv) {
+    const int nb = kDiagNB;
+    c128* dL = dinv;
+    c128* dU = dinv + (size_t)n * nb;
+    const int64_t total = 2 * n * nb;
+    int64_t gq = (total + 255) / 256, cap = (int64_t)kNumSMs * 16;
+    set_identity_blocks_kernel<<<(int)(gq < cap ? gq : cap), 256, 0, ctx->stream>>>(2 * n, nb, dinv);  // n % nb == 0 not required:
+    KLAUNCH_CHECK(ctx);                                                                                // see the re-init below
+    if (n % nb != 0) {
+        // the U half starts at row n which may not be a multiple of nb: initialise it separately
+        int64_t g2 = (n * nb + 255) / 256;
+        set_identity_blocks_kernel<<<(int)(g2 < cap ? g2 : cap), 256, 0, ctx->stream>>>(n, nb, dU);
+        KLAUNCH_CHECK(ctx);
+    }
+    for (int64_t k0 = 0; k0 < n; k0 += nb) {
+        const int h = (int)((n - k0) < nb ? (n - k0) : nb);
+        const c128* Dkk = LU + k0 * n + k0;
+        FEAST_TRY((trsm_rec<true, true>(ctx, h, h, Dkk, n, 1, false, dL + k0 * nb, nb, 1)));
+        FEAST_TRY((trsm_rec<false, false>(ctx, h, h, Dkk, n, 1, false, dU + k0 * nb, nb, 1)));
+    }
+    return 0;
+}
+
+int dense_getrs(feast_ctx* ctx, int64_t n, const c128* LU, const int* perm_d, const c128* dinv, int m, const c128* Rhs,
+                c128* Y, bool conj_transpose) {
     const int64_t total = n * m;
     int64_t g = (total + 255) / 256, cap = (int64_t)kNumSMs * 16;
     const int grid = (int)(g < cap ? (g < 1 ? 1 : g) : cap);
@@ -354,15 +401,43 @@ int dense_getrs(feast_ctx* ctx, int64_t n, const c128* LU, const int* perm_d, in
         // Y = P * Rhs ; L w = Y ; U y = w      (A = P^T L U  ->  A^-1 = U^-1 L^-1 P)
         permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(n, m, Rhs, Y, perm_d, 0);
         KLAUNCH_CHECK(ctx);
-        FEAST_TRY((trsm_rec<true, true>(ctx, (int)n, m, LU, 1, n, false, Y, m, 1)));
-        FEAST_TRY((trsm_rec<false, false>(ctx, (int)n, m, LU, 1, n, false, Y, m, 1)));
+        if (dinv && ctx->W2.p) {
+            // blocked solves: W_k = inv(L_kk) Y_k ; Y_below -= L[below,k] W_k ; then Y_k = inv(U_kk) W_k ;
+            // W_above -= U[above,k] Y_k.  Two DMMA GEMMs per diagonal block, ping-ponging Y <-> W.
+            const int nb = kDiagNB;
+            c128* W = ctx->W2.p;
+            const c128* dL = dinv;
+            const c128* dU = dinv + (size_t)n * nb;
+            for (int64_t k0 = 0; k0 < n; k0 += nb) {
+                const int h = (int)((n - k0) < nb ? (n - k0) : nb);
+                FEAST_TRY(launch_zgemm(ctx, h, m, h, hc128(1, 0), dL + k0 * nb, nb, 1, false, Y + k0 * m, m, 1, hc128(0, 0),
+                                       W + k0 * m, m, 1));
+                const int below = (int)(n - k0 - h);
+                if (below > 0)
+                    FEAST_TRY(launch_zgemm(ctx, below, m, h, hc128(-1, 0), LU + (k0 + h) * n + k0, n, 1, false, W + k0 * m, m, 1,
+                                           hc128(1, 0), Y + (k0 + h) * m, m, 1));
+            }
+            const int64_t nblk = (n + nb - 1) / nb;
+            for (int64_t kb = nblk - 1; kb >= 0; --kb) {
+                const int64_t k0 = kb * nb;
+                const int h = (int)((n - k0) < nb ? (n - k0) : nb);
+                FEAST_TRY(launch_zgemm(ctx, h, m, h, hc128(1, 0), dU + k0 * nb, nb, 1, false, W + k0 * m, m, 1, hc128(0, 0),
+                                       Y + k0 * m, m, 1));
+                if (k0 > 0)
+                    FEAST_TRY(launch_zgemm(ctx, (int)k0, m, h, hc128(-1, 0), LU + k0, n, 1, false, Y + k0 * m, m, 1, hc128(1, 0),
+                                           W, m, 1));
+            }
+            return 0;
+        }
+        FEAST_TRY((trsm_rec<true, true>(ctx, (int)n, m, LU, n, 1, false, Y, m, 1)));
+        FEAST_TRY((trsm_rec<false, false>(ctx, (int)n, m, LU, n, 1, false, Y, m, 1)));
     } else {
         // A^H = U^H L^H P : U^H w = b (lower, non-unit, conj) ; L^H v = w (upper, unit, conj) ; y = P^T v
         c128* tmp = ctx->W2.p;
         CUDA_TRY(ctx, cudaMemcpyAsync(tmp, Rhs, sizeof(c128) * total, cudaMemcpyDeviceToDevice, ctx->stream));
         // T := U^H : T(i,k) = conj(U(k,i)) -> strides swapped
-        FEAST_TRY((trsm_rec<true, false>(ctx, (int)n, m, LU, n, 1, true, tmp, m, 1)));
-        FEAST_TRY((trsm_rec<false, true>(ctx, (int)n, m, LU, n, 1, true, tmp, m, 1)));
+        FEAST_TRY((trsm_rec<true, false>(ctx, (int)n, m, LU, 1, n, true, tmp, m, 1)));
+        FEAST_TRY((trsm_rec<false, true>(ctx, (int)n, m, LU, 1, n, true, tmp, m, 1)));
         permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(n, m, tmp, Y, perm_d, 1);
         KLAUNCH_CHECK(ctx);
     }

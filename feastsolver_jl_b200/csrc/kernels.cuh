@@ -64,12 +64,14 @@ int gmres_solve(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, dou
 size_t gmres_small_bytes(int m, int R);
 
 // ---- dense.cu ------------------------------------------------------------------
-// In-place LU with partial pivoting of column-major n x n Z (zgetrf layout); ipiv device 0-based.
+// In-place LU with partial pivoting of ROW-major n x n Z (Z(i,j) = Z[i*n + j]); ipiv device 0-based.
 int dense_getrf(feast_ctx* ctx, int64_t n, c128* Z, int* ipiv_d, int* info_out);
 // Solve op(LU) Y = Rhs for m right-hand sides held ROW-MAJOR (n x m); result in Y (row-major).
 // perm_d from dense_build_perm (perm[i] = source row of permuted row i).
-int dense_getrs(feast_ctx* ctx, int64_t n, const c128* LU, const int* perm_d, int m, const c128* Rhs, c128* Y,
-                bool conj_transpose);
+// dinv: diagonal-block inverses from dense_build_diag_inverses (may be nullptr -> recursive TRSM)
+int dense_getrs(feast_ctx* ctx, int64_t n, const c128* LU, const int* perm_d, const c128* dinv, int m, const c128* Rhs,
+                c128* Y, bool conj_transpose);
+int dense_build_diag_inverses(feast_ctx* ctx, int64_t n, const c128* LU, c128* dinv);
 int dense_build_perm(feast_ctx* ctx, int64_t n, const int* ipiv_d, int* perm_d);
 size_t spmm_partials_bytes(int m);
 int debug_check_finite(feast_ctx* ctx, const void* p, int64_t ndoubles, const char* name);

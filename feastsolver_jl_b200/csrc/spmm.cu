@@ -207,7 +207,7 @@ __global__ void scatter_dense_kernel(int n, const int* __restrict__ rowptr, cons
     // one warp per row; Z pre-zeroed
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
-    for (int e = rowptr[warp] + lane; e < rowptr[warp + 1]; e += 32) Z[(int64_t)col[e] * n + warp] = zvals[e];
+    for (int e = rowptr[warp] + lane; e < rowptr[warp + 1]; e += 32) Z[(int64_t)warp * n + col[e]] = zvals[e];  // row-major
 }
 
 // R[row, j] = sum_e ( sum_i lam_j^i a_i[e] ) X[col_e, j]   -- one pass over X, Horner per column
