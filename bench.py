@@ -264,6 +264,13 @@ def run_ours(args):
     value = NODES * args.steps / (ms / 1e3)
     ctx.close()
 
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"metric": "contour_node_solves_per_sec", "value": value, "ms_per_step": ms / args.steps,
+                              "spmm_ms_per_launch": spmm_ms, "gpu_launches": launches, "note": "profiling run (--no-e2e)"}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- e2e: public API with host buffers, run to convergence (time-to-solution) ----
     st_e2e = {}
     Xh = X0.copy()
@@ -336,6 +343,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=GRID, help="grid points per dimension (default: the C2 size 100)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 0)

@@ -50,10 +50,11 @@ __global__ void cocg_alpha_kernel(int m, KryScal s) {
     }
 }
 
-// x += alpha p ; r -= alpha q ; partials of <r,r> (unconjugated) and ||r||^2
+// r -= alpha q ; partials of <r,r> (unconjugated) and ||r||^2.  (x += alpha p is deferred to the
+// direction kernel, which reads p anyway: 3 + 5 block passes instead of 6 + 3.)
 __global__ void __launch_bounds__(256)
-cocg_update_kernel(int64_t n, int m, c128* __restrict__ x, c128* __restrict__ r, const c128* __restrict__ p,
-                   const c128* __restrict__ q, KryScal s, double* __restrict__ partials) {
+cocg_update_kernel(int64_t n, int m, c128* __restrict__ r, const c128* __restrict__ q, KryScal s,
+                   double* __restrict__ partials) {
     extern __shared__ double sm[];  // [256][3]
     int cw = 1;
     while (cw < m && cw < 256) cw <<= 1;
@@ -63,15 +64,12 @@ cocg_update_kernel(int64_t n, int m, c128* __restrict__ x, c128* __restrict__ r,
         double re = 0.0, im = 0.0, nn = 0.0;
         if (j < m) {
             const c128 a = s.alpha[j];
+            const c128 na = cmake(-a.x, -a.y);
             const bool act = s.active[j] != 0;
             for (int64_t i = (int64_t)blockIdx.x * rpp + rr; i < n; i += (int64_t)gridDim.x * rpp) {
                 const int64_t t = i * m + j;
                 c128 rv = r[t];
                 if (act) {
-                    c128 xv = x[t];
-                    cfma(xv, a, __ldg(p + t));
-                    x[t] = xv;
-                    const c128 na = cmake(-a.x, -a.y);
                     cfma(rv, na, __ldg(q + t));
                     r[t] = rv;
                 }
@@ -93,18 +91,25 @@ cocg_update_kernel(int64_t n, int m, c128* __restrict__ x, c128* __restrict__ r,
     }
 }
 
-// reduce partials -> rho', ||r||^2 ; beta = rho'/rho ; convergence bookkeeping
-__global__ void cocg_beta_kernel(int m, int nblocks, const double* __restrict__ partials, KryScal s, double tol2) {
+// reduce partials -> rho', ||r||^2 ; beta = rho'/rho ; convergence bookkeeping.
+// One CTA of 1024 threads: a warp sums one of the 3m outputs at a time (lanes stride over the
+// partial blocks), then the first m threads do the per-column scalar recurrences.
+__global__ void __launch_bounds__(1024) cocg_beta_kernel(int m, int nblocks, const double* __restrict__ partials, KryScal s,
+                                                         double tol2) {
+    extern __shared__ double red[];  // [3m]
     __shared__ int cnt;
     __shared__ double rmax;
     if (threadIdx.x == 0) { cnt = 0; rmax = 0.0; }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int o = warp; o < 3 * m; o += nw) {
+        double v = 0.0;
+        for (int b = lane; b < nblocks; b += 32) v += partials[(int64_t)b * 3 * m + o];
+        for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[o] = v;
+    }
     __syncthreads();
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
-        double re = 0.0, im = 0.0, nn = 0.0;
-        for (int b = 0; b < nblocks; ++b) {
-            const double* o = partials + (int64_t)b * 3 * m + 3 * j;
-            re += o[0]; im += o[1]; nn += o[2];
-        }
+        const double re = red[3 * j], im = red[3 * j + 1], nn = red[3 * j + 2];
         s.rn2[j] = nn;
         c128 beta = cmake(0.0, 0.0);
         if (s.active[j]) {
@@ -130,14 +135,22 @@ __global__ void cocg_beta_kernel(int m, int nblocks, const double* __restrict__ 
     if (threadIdx.x == 0) { *s.nactive = cnt; *s.relmax = rmax; }
 }
 
-// p = r + beta p (active columns only)
-__global__ void cocg_p_kernel(int64_t total, int m, c128* __restrict__ p, const c128* __restrict__ r, KryScal s) {
+// x += alpha p (columns that were active in this iteration: alpha != 0) ; p = r + beta p (still active)
+__global__ void cocg_p_kernel(int64_t total, int m, c128* __restrict__ x, c128* __restrict__ p, const c128* __restrict__ r,
+                              KryScal s) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int j = (int)(t % m);
-        if (!s.active[j]) continue;
-        c128 v = __ldg(r + t);
-        cfma(v, s.beta[j], p[t]);
-        p[t] = v;
+        const c128 a = s.alpha[j];
+        if (a.x == 0.0 && a.y == 0.0) continue;      // frozen before this iteration: nothing to do
+        const c128 pv = p[t];
+        c128 xv = x[t];
+        cfma(xv, a, pv);
+        x[t] = xv;
+        if (s.active[j]) {
+            c128 v = __ldg(r + t);
+            cfma(v, s.beta[j], pv);
+            p[t] = v;
+        }
     }
 }
 
@@ -324,11 +337,11 @@ int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs,
             TIMED_SPMM(launch_spmm(ctx, n, m, ctx->u_rowptr, ctx->u_col, nullptr, zvals, p, m, q, m, s.mu));
             cocg_alpha_kernel<<<1, 128, 0, st>>>(m, s);
             KLAUNCH_CHECK(ctx);
-            cocg_update_kernel<<<rgrid, 256, 768 * sizeof(double), st>>>(n, m, x, r, p, q, s, ctx->red_d);
+            cocg_update_kernel<<<rgrid, 256, 768 * sizeof(double), st>>>(n, m, r, q, s, ctx->red_d);
             KLAUNCH_CHECK(ctx);
-            cocg_beta_kernel<<<1, 128, 0, st>>>(m, rgrid, ctx->red_d, s, tol2);
+            cocg_beta_kernel<<<1, 1024, 3 * m * sizeof(double), st>>>(m, rgrid, ctx->red_d, s, tol2);
             KLAUNCH_CHECK(ctx);
-            cocg_p_kernel<<<ew_grid_k(total), 256, 0, st>>>(total, m, p, r, s);
+            cocg_p_kernel<<<ew_grid_k(total), 256, 0, st>>>(total, m, x, p, r, s);
             KLAUNCH_CHECK(ctx);
             ++iters;
             if (iters % check_every == 0 || iters == maxit) {

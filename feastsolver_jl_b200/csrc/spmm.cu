@@ -113,13 +113,16 @@ spmm_csr_kernel(int n, int m, const int* __restrict__ rowptr, const int* __restr
     }
 }
 
+// one warp per output: lanes stride over the partial blocks (a single thread walking ~600 partials
+// cost 55 us per launch in the first ncu launch list)
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int nblocks, int count,
                                        double* __restrict__ out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (o >= count) return;
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partials[(int64_t)b * count + t];
-    out[t] = s;
+    for (int b = lane; b < nblocks; b += 32) s += partials[(int64_t)b * count + o];
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) out[o] = s;
 }
 
 template <typename VT, int G, int CPL>
@@ -129,7 +132,7 @@ int spmm_dispatch_dot(feast_ctx* ctx, int grid, int n, int m, const int* rowptr,
         spmm_csr_kernel<VT, G, CPL, true><<<grid, kSpmmThreads, 0, ctx->stream>>>(
             n, m, rowptr, col, val, X, ldx, Y, ldy, ctx->red_d);
         KLAUNCH_CHECK(ctx);
-        reduce_partials_kernel<<<ceil_div(2 * m, 128), 128, 0, ctx->stream>>>(ctx->red_d, grid, 2 * m,
+        reduce_partials_kernel<<<ceil_div(2 * m * 32, 128), 128, 0, ctx->stream>>>(ctx->red_d, grid, 2 * m,
                                                                               (double*)dot_out);
         KLAUNCH_CHECK(ctx);
     } else {
@@ -330,7 +333,7 @@ int launch_poly_residual(feast_ctx* ctx, int64_t n, int m, int nslots, const int
         if (grid < 1) grid = 1;
         poly_fro_kernel<<<grid, 256, sizeof(double) * m, ctx->stream>>>(unnz, m, a, lam_d, ctx->red_d);
         KLAUNCH_CHECK(ctx);
-        reduce_partials_kernel<<<ceil_div(m, 128), 128, 0, ctx->stream>>>(ctx->red_d, grid, m, fro2_d);
+        reduce_partials_kernel<<<ceil_div(m * 32, 128), 128, 0, ctx->stream>>>(ctx->red_d, grid, m, fro2_d);
         KLAUNCH_CHECK(ctx);
     }
     return 0;
