@@ -7,6 +7,7 @@
 //   * optional fused <X, S X> column reduction via warp shuffles (the COCG <p, Zp>).
 // Replaces Julia's CSC mul! (src/feast.jl:42,118,120; src/utils.jl:114) and the
 // per-column `T(l_j) * x_j` of src/utils.jl:104-109.
+#include <stdlib.h>
 #include "kernels.cuh"
 
 namespace {
@@ -22,8 +23,8 @@ template <> struct ValOps<c128> {
 constexpr int kSpmmThreads = 256;
 
 // partials layout: [gridDim.x][2*m] doubles
-template <typename VT, int G, int CPL, bool DOT>
-__global__ void __launch_bounds__(kSpmmThreads)
+template <typename VT, int G, int CPL, bool DOT, int MINB>
+__global__ void __launch_bounds__(kSpmmThreads, MINB)
 spmm_csr_kernel(int n, int m, const int* __restrict__ rowptr, const int* __restrict__ col,
                 const VT* __restrict__ val, const c128* __restrict__ X, int ldx, c128* __restrict__ Y, int ldy,
                 double* __restrict__ partials) {
@@ -125,22 +126,32 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partials, int 
     if (lane == 0) out[o] = s;
 }
 
-template <typename VT, int G, int CPL>
-int spmm_dispatch_dot(feast_ctx* ctx, int grid, int n, int m, const int* rowptr, const int* col, const VT* val,
-                      const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
+template <typename VT, int G, int CPL, int MINB>
+int spmm_launch_minb(feast_ctx* ctx, int grid, int n, int m, const int* rowptr, const int* col, const VT* val,
+                     const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
     if (dot_out) {
-        spmm_csr_kernel<VT, G, CPL, true><<<grid, kSpmmThreads, 0, ctx->stream>>>(
+        spmm_csr_kernel<VT, G, CPL, true, MINB><<<grid, kSpmmThreads, 0, ctx->stream>>>(
             n, m, rowptr, col, val, X, ldx, Y, ldy, ctx->red_d);
         KLAUNCH_CHECK(ctx);
         reduce_partials_kernel<<<ceil_div(2 * m * 32, 128), 128, 0, ctx->stream>>>(ctx->red_d, grid, 2 * m,
-                                                                              (double*)dot_out);
+                                                                                   (double*)dot_out);
         KLAUNCH_CHECK(ctx);
     } else {
-        spmm_csr_kernel<VT, G, CPL, false><<<grid, kSpmmThreads, 0, ctx->stream>>>(
+        spmm_csr_kernel<VT, G, CPL, false, MINB><<<grid, kSpmmThreads, 0, ctx->stream>>>(
             n, m, rowptr, col, val, X, ldx, Y, ldy, nullptr);
         KLAUNCH_CHECK(ctx);
     }
     return 0;
+}
+
+template <typename VT, int G, int CPL>
+int spmm_dispatch_dot(feast_ctx* ctx, int grid, int n, int m, const int* rowptr, const int* col, const VT* val,
+                      const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
+    static const int minb = getenv("FEAST_SPMM_MINB") ? atoi(getenv("FEAST_SPMM_MINB")) : 4;
+    if (G == 32 && minb == 5) return spmm_launch_minb<VT, G, CPL, 5>(ctx, grid, n, m, rowptr, col, val, X, ldx, Y, ldy, dot_out);
+    if (G == 32 && minb == 6) return spmm_launch_minb<VT, G, CPL, 6>(ctx, grid, n, m, rowptr, col, val, X, ldx, Y, ldy, dot_out);
+    if (G == 32 && minb == 3) return spmm_launch_minb<VT, G, CPL, 3>(ctx, grid, n, m, rowptr, col, val, X, ldx, Y, ldy, dot_out);
+    return spmm_launch_minb<VT, G, CPL, 4>(ctx, grid, n, m, rowptr, col, val, X, ldx, Y, ldy, dot_out);
 }
 
 template <typename VT>
@@ -152,7 +163,7 @@ int spmm_dispatch(feast_ctx* ctx, int n, int m, const int* rowptr, const int* co
         int64_t need = (n + rows_per_block - 1) / rows_per_block;
         int64_t cap = (int64_t)kNumSMs * 8;
         int64_t g = need < cap ? need : cap;
-        if (dot_out) { int64_t capd = (int64_t)kNumSMs * 4; if (g > capd) g = capd; }
+        // (the fused-dot variant used to be capped at 4 CTAs/SM: ncu showed it latency-bound at 32 warps/SM)
         return (int)(g < 1 ? 1 : g);
     };
 #define SPMM_CASE(G, CPL) return spmm_dispatch_dot<VT, G, CPL>(ctx, grid_for(G), n, m, rowptr, col, val, X, ldx, Y, ldy, dot_out)
