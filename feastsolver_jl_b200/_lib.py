@@ -74,6 +74,7 @@ SIGNATURES = {
     "feast_contour_apply": (_i, [_vp, _vp, _i, C.POINTER(FeastStats)]),
     "feast_beyn_reduce": (_i, [_vp, _vp, _vp]),
     "feast_orthonormalize_X": (_i, [_vp]),
+    "feast_estimate_count": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(FeastStats)]),
     "feast_factorize": (_i, [_vp, _vp, _i, C.POINTER(_vp)]),
     "feast_solve": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _i64, _i]),
     "feast_factor_free": (_i, [_vp, _vp]),

@@ -428,6 +428,50 @@ int download_block(feast_ctx* ctx, const BlockVec& b, feast_c128* H, int64_t ld)
     return 0;
 }
 
+// One shifted solve  (sum_i coef[i] slot_i) Y = rhs  with m0 right-hand sides: dense LU (stored per node
+// when store != 0, node index k >= 0) or Krylov on the union pattern.  `e1` is recorded between the
+// factorisation/assembly and the solve.  This is linsolve! (src/utils.jl:175-179) for one contour node.
+int solve_shifted(feast_ctx* ctx, int solver, int method, int k, const hc128* coef, const c128* rhs, c128* Y,
+                  feast_stats& st, cudaEvent_t e1, int* rc_final) {
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    if (solver == FEAST_SOLVER_DENSE_LU) {
+        DenseLU* f;
+        DenseLU scratch;
+        bool need_factor = true;
+        if (ctx->store && k >= 0) {
+            f = &ctx->stored[k];
+            need_factor = (f->lu == nullptr);
+        } else {
+            if (!ctx->zdense) FEAST_TRY(dev_alloc(ctx, &ctx->zdense, (size_t)n * n));
+            if (!ctx->zpiv) FEAST_TRY(dev_alloc(ctx, &ctx->zpiv, (size_t)2 * n));
+            if (!ctx->zdinv) FEAST_TRY(dev_alloc(ctx, &ctx->zdinv, (size_t)2 * n * kDiagNB));
+            scratch.lu = ctx->zdense; scratch.ipiv = ctx->zpiv; scratch.perm = ctx->zpiv + n; scratch.dinv = ctx->zdinv;
+            f = &scratch;
+        }
+        if (need_factor) {
+            int info = 0;
+            FEAST_TRY(factor_dense(ctx, coef, *f, &info));                                // feast.jl:36 / :65 lu
+            if (info && !st.info) st.info = info;
+        }
+        if (e1) cudaEventRecord(e1, ctx->stream);
+        FEAST_TRY(ensure_block(ctx, ctx->W2));
+        FEAST_TRY(dense_getrs(ctx, n, f->lu, f->perm, f->dinv, m, rhs, Y, false));        // ldiv!
+    } else {
+        FEAST_TRY(assemble_sparse_Z(ctx, coef, ctx->zvals));
+        if (e1) cudaEventRecord(e1, ctx->stream);
+        KrylovResult kr;
+        FEAST_TRY(krylov_solve(ctx, method, ctx->zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, &kr));
+        st.inner_iters_total += kr.iters;
+        st.inner_iters_max = std::max(st.inner_iters_max, kr.iters);
+        st.inner_relres_max = std::max(st.inner_relres_max, kr.relres_max);
+        st.t_spmm_ms += kr.spmm_ms;
+        st.spmm_launches += kr.spmm_launches;
+        if (!kr.converged) *rc_final = FEAST_WARN_INNER_MAXIT;
+    }
+    return 0;
+}
+
 }  // namespace
 
 // =============================================================================== ABI
@@ -849,40 +893,7 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
             d[j] = first_pass ? w : w / (z - hc128(lambda[j].re, lambda[j].im));              // feast.jl:60,69
         CUDA_TRY(ctx, cudaMemcpyAsync(d_d, d.data(), sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
         cudaEventRecord(e0, ctx->stream);
-        if (solver == FEAST_SOLVER_DENSE_LU) {
-            DenseLU* f;
-            DenseLU scratch;
-            bool need_factor = true;
-            if (ctx->store) {
-                f = &ctx->stored[k];
-                need_factor = (f->lu == nullptr);
-            } else {
-                if (!ctx->zdense) FEAST_TRY(dev_alloc(ctx, &ctx->zdense, (size_t)n * n));
-                if (!ctx->zpiv) FEAST_TRY(dev_alloc(ctx, &ctx->zpiv, (size_t)2 * n));
-                if (!ctx->zdinv) FEAST_TRY(dev_alloc(ctx, &ctx->zdinv, (size_t)2 * n * kDiagNB));
-                scratch.lu = ctx->zdense; scratch.ipiv = ctx->zpiv; scratch.perm = ctx->zpiv + n; scratch.dinv = ctx->zdinv;
-                f = &scratch;
-            }
-            if (need_factor) {
-                int info = 0;
-                FEAST_TRY(factor_dense(ctx, coef, *f, &info));                                // feast.jl:36 / :65 lu
-                if (info && !st.info) st.info = info;
-            }
-            cudaEventRecord(e1, ctx->stream);
-            FEAST_TRY(ensure_block(ctx, ctx->W2));
-            FEAST_TRY(dense_getrs(ctx, n, f->lu, f->perm, f->dinv, m, rhs, ctx->W1.p, false));         // ldiv!
-        } else {
-            FEAST_TRY(assemble_sparse_Z(ctx, coef, ctx->zvals));
-            cudaEventRecord(e1, ctx->stream);
-            KrylovResult kr;
-            FEAST_TRY(krylov_solve(ctx, method, ctx->zvals, rhs, ctx->W1.p, ctx->inner_tol, ctx->max_inner, &kr));
-            st.inner_iters_total += kr.iters;
-            st.inner_iters_max = std::max(st.inner_iters_max, kr.iters);
-            st.inner_relres_max = std::max(st.inner_relres_max, kr.relres_max);
-            st.t_spmm_ms += kr.spmm_ms;
-            st.spmm_launches += kr.spmm_launches;
-            if (!kr.converged) rc_final = FEAST_WARN_INNER_MAXIT;
-        }
+        FEAST_TRY(solve_shifted(ctx, solver, method, k, coef, rhs, ctx->W1.p, st, e1, &rc_final));
         debug_check_finite(ctx, rhs, 2 * n * m, "contour: rhs");
         debug_check_finite(ctx, ctx->W1.p, 2 * n * m, "contour: solve result");
         // Q += (X - Y) diag(w/(z - l))  [feast.jl:68-70] ; polynomial: Q0, Q1 [nlfeast.jl:56-58]
@@ -916,6 +927,58 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
     if (rc_final == FEAST_WARN_INNER_MAXIT)
         feast_fail(ctx, FEAST_WARN_INNER_MAXIT, "Krylov inner solve stopped at max_inner=%d (relres %.3e)", ctx->max_inner,
                    st.inner_relres_max);
+    return rc_final;
+}
+
+// Stochastic eigenvalue-count estimate (src/stochastic.jl:2-33): the current subspace block X holds the
+// probe vectors; est = Re sum_k w_k tr(X' (z_k B - A)^-1 X) / m0, node-sharded like the contour loop.
+int feast_estimate_count(feast_ctx* ctx, double* est, feast_stats* stats) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, est != nullptr, 2, "null output");
+    if (ctx->problem == FEAST_PROBLEM_POLYNOMIAL)
+        return feast_fail(ctx, FEAST_ERR_STATE, "feast_estimate_count applies to linear problems");
+    if (ctx->znodes.empty()) return feast_fail(ctx, FEAST_ERR_STATE, "feast_set_contour has not been called");
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    const int solver = effective_solver(ctx), method = effective_krylov(ctx);
+    if (solver == FEAST_SOLVER_KRYLOV && ctx->storage_dense)
+        return feast_fail(ctx, FEAST_ERR_STATE, "Krylov inner solves need sparse operators");
+    FEAST_TRY(ensure_block(ctx, ctx->W1));
+    if (solver == FEAST_SOLVER_KRYLOV) FEAST_TRY(ensure_krylov_work(ctx, method));
+    const int nnodes = (int)ctx->znodes.size();
+    if (ctx->store && (int)ctx->stored.size() != nnodes) ctx->stored.resize(nnodes);
+    feast_stats st;
+    memset(&st, 0, sizeof(st));
+    int rc_final = 0;
+    c128* dots_d = ctx->small_d;   // m complex
+    hc128 acc(0.0, 0.0);
+    std::vector<hc128> dots(m);
+    for (int k = 0; k < nnodes; ++k) {
+        if (ctx->owner[k] != ctx->rank) continue;
+        st.nodes_local++;
+        const hc128 z = ctx->znodes[k], w = ctx->zweights[k];
+        hc128 coef[FEAST_MAX_SLOTS] = {hc128(-1, 0), z};                     // B z - A  (stochastic.jl:24)
+        FEAST_TRY(solve_shifted(ctx, solver, method, ctx->store ? -1 : -1, coef, ctx->X.p, ctx->W1.p, st, nullptr, &rc_final));
+        FEAST_TRY(launch_coldot(ctx, n, m, ctx->X.p, ctx->W1.p, true, dots_d));   // diag of X' Y  (tr(P), :26-27)
+        CUDA_TRY(ctx, cudaMemcpyAsync(dots.data(), dots_d, sizeof(c128) * m, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        hc128 tr(0.0, 0.0);
+        for (int j = 0; j < m; ++j) tr += dots[j];
+        acc += tr * w / (double)m;
+    }
+    double part[2] = {acc.real(), acc.imag()};
+    if (ctx->nranks > 1) {
+        const NcclApi* api = nccl_api();
+        double* buf = (double*)ctx->small_d;
+        CUDA_TRY(ctx, cudaMemcpyAsync(buf, part, sizeof(part), cudaMemcpyHostToDevice, ctx->stream));
+        int rc = api->AllReduce(buf, buf, 2, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
+        if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclAllReduce failed");
+        CUDA_TRY(ctx, cudaMemcpyAsync(part, buf, sizeof(part), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *est = part[0];                                                          // return real(est), :32
+    if (stats) *stats = st;
+    if (st.info) return feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d of a shifted factorisation", st.info);
     return rc_final;
 }
 

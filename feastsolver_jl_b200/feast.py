@@ -174,6 +174,14 @@ class FeastContext:
         self._ck(self.lib.feast_sync(self.h))
         return Rf, G1
 
+    def estimate_count(self):
+        est = C.c_double(0.0)
+        st = FeastStats()
+        rc = self.lib.feast_estimate_count(self.h, C.byref(est), C.byref(st))
+        self._ck(rc, allow=(0, _lib.FEAST_WARN_INNER_MAXIT))
+        self.last_stats = st.as_dict()
+        return float(est.value)
+
     def orthonormalize_X(self):
         self._ck(self.lib.feast_orthonormalize_X(self.h))
 
@@ -414,3 +422,41 @@ def nlfeast(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=1
         if own_ctx:
             ctx.close()
     return Lam, X, res
+
+
+def contour_estimate_eig(A, contour, B=I, *, samples=None, eps=1e-12, debug=False, mixed_prec=False,
+                         factorizer=None, left_divider=None, X=None, seed=0, ctx=None, solver_opts=None, comm=None):
+    """contour_estimate_eig(A, contour, B=I; samples=min(100, N), ...)  (src/stochastic.jl:2-33):
+    Hutchinson estimate of the number of eigenvalues inside the contour,
+    real(sum_k w_k tr(X' (z_k B - A)^-1 X) / samples) with X = randn(ComplexF64, N, samples).
+    `X` may be passed explicitly (parity tests ship the probe block as data)."""
+    _check_plugins(factorizer, left_divider, mixed_prec)
+    N = A.shape[0]
+    m0 = min(100, N) if samples is None else int(samples)
+    if X is None:
+        rng = np.random.default_rng(seed)
+        X = (rng.standard_normal((N, m0)) + 1j * rng.standard_normal((N, m0))) / np.sqrt(2.0)
+    own_ctx = ctx is None
+    if own_ctx:
+        ctx = FeastContext()
+    try:
+        generalized = not (B is None or isinstance(B, str))
+        if generalized:
+            A, B = _densify_if_mixed(A, B)
+        ctx.set_operator(0, A)
+        if generalized:
+            ctx.set_operator(1, B, n=N)
+            ctx.set_problem(_lib.PROBLEM_GENERALIZED, 2, N)
+        else:
+            ctx.set_problem(_lib.PROBLEM_STANDARD, 1, N)
+        if comm is not None:
+            comm(ctx)
+        ctx.set_contour(contour.nodes, contour.weights)
+        if ctx.nranks > 1:
+            ctx.set_node_owners(node_owners(contour.nodes, ctx.nranks))
+        ctx.set_solver(**(solver_opts or {}))
+        ctx.set_subspace(X)
+        return ctx.estimate_count()
+    finally:
+        if own_ctx:
+            ctx.close()

@@ -149,6 +149,9 @@ FEAST_API int  feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int
  * finishes the m0 x m0 SVD/eig (utils.jl:72-76) and calls feast_recover_residual
  * with Xq = Ur * vecs.                                                          */
 FEAST_API int  feast_beyn_reduce(feast_ctx* ctx, feast_c128* Rf, feast_c128* G1);
+/* contour_estimate_eig (src/stochastic.jl:2-33): with the probe vectors uploaded by
+ * feast_set_subspace, est = Re sum_k w_k tr(X' (z_k B - A)^-1 X) / m0 (node-sharded).   */
+FEAST_API int  feast_estimate_count(feast_ctx* ctx, double* est, feast_stats* stats);
 /* nlfeast! first statement: X <- thin Q of X (src/nlfeast.jl:12-13).           */
 FEAST_API int  feast_orthonormalize_X(feast_ctx* ctx);
 

@@ -544,6 +544,7 @@ def contour_estimate_eig(A, contour, B=None, *, samples=None, rng=None, X=None):
     if X is None:
         rng = np.random.default_rng(0) if rng is None else rng
         X = (rng.standard_normal((N, m0)) + 1j * rng.standard_normal((N, m0))) / np.sqrt(2)
+    m0 = X.shape[1]  # `samples` is the number of probe columns (stochastic.jl:7,27)
     sparse = _is_sparse(A)
     Ac = A.astype(complex) if sparse else np.asarray(A, dtype=complex)
     if B is None:

@@ -1,0 +1,39 @@
+"""Config C4 (BASELINE.json): nlfeast! on the quartic butterfly-structured polynomial NEP scaled to
+mb x mb one-dimensional blocks (n = mb^2, sparse 5-point patterns), circle + trapezoid nodes.
+
+    python scripts/c4_run.py --mb 100 --m0 48 --nodes 24 --r 0.05
+"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import feastsolver_jl_b200 as fs
+from feastsolver_jl_b200 import _lib, workloads as wl
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--mb", type=int, default=100)
+ap.add_argument("--m0", type=int, default=48)
+ap.add_argument("--nodes", type=int, default=24)
+ap.add_argument("--r", type=float, default=0.05)
+ap.add_argument("--iter", type=int, default=12)
+ap.add_argument("--tol", type=float, default=1e-8)
+ap.add_argument("--maxit", type=int, default=2000)
+ap.add_argument("--solver", default="auto", choices=["auto", "dense", "krylov"])
+a = ap.parse_args()
+coeffs = wl.butterfly_coeffs(a.mb)
+n = a.mb ** 2
+X0 = wl.rand_subspace(n, a.m0, seed=0)
+kind = {"auto": _lib.SOLVER_AUTO, "dense": _lib.SOLVER_DENSE_LU, "krylov": _lib.SOLVER_KRYLOV}[a.solver]
+st = {}
+t0 = time.perf_counter()
+lam, X, res = fs.nlfeast(coeffs, X0, a.nodes, a.iter, c=1 + 1j, r=a.r, eps=1e-10, stats=st,
+                         solver_opts={"kind": kind, "inner_tol": a.tol, "max_inner": a.maxit})
+tts = time.perf_counter() - t0
+inside = np.abs(lam - (1 + 1j)) <= a.r
+good = inside & (res < 1e-8)
+hist = st["history"]
+print(json.dumps({"config": f"C4 butterfly quartic n={n} nnz={coeffs[0].nnz} m0={a.m0} nodes={a.nodes} r={a.r} solver={a.solver}",
+                  "inside": int(inside.sum()), "converged_inside": int(good.sum()),
+                  "max_res_converged": float(res[good].max()) if good.any() else None, "outer_iterations": len(hist),
+                  "tts_s": tts, "inner_iters": [h.get("inner_iters_total") for h in hist],
+                  "inner_relres_max": [h.get("inner_relres_max") for h in hist],
+                  "res_history": [h.get("max_res_inside") for h in hist]}))

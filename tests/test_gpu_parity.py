@@ -383,6 +383,26 @@ def test_system5_quadratic_kernels(fs, nep_fixtures):
     assert nep_fixtures["system5_companion_inside"].size == 50  # companion() count for the script's contour
 
 
+def test_contour_estimate_eig_matches_oracle(fs):
+    """src/stochastic.jl:2-33 / test/contour_test.jl:7-32 shape: same probe block X on both sides."""
+    from feastsolver_jl_b200 import _lib
+    n = 1000
+    A = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(n, n), format="csc")
+    X = (np.random.default_rng(3).standard_normal((n, 60)) + 1j * np.random.default_rng(4).standard_normal((n, 60))) / np.sqrt(2)
+    for ct_o, ct_g in [(fo.circular_contour_trapezoidal(0.05 + 0j, 0.05, 16), fs.circular_contour_trapezoidal(0.05 + 0j, 0.05, 16)),
+                       (fo.rectangular_contour_gauss(0.0 - 0.02j, 0.1 + 0.02j, 16), fs.rectangular_contour_gauss(0.0 - 0.02j, 0.1 + 0.02j, 16))]:
+        ref = fo.contour_estimate_eig(A, ct_o, X=X.copy())
+        got = fs.contour_estimate_eig(A, ct_g, X=X.copy())
+        assert abs(got - ref) <= 1e-9 * max(1.0, abs(ref))
+    exact = np.sum(2 - 2 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1)) <= 0.1)
+    assert abs(got - exact) < 0.4 * exact + 3
+    # generalized pencil + Krylov inner solves
+    Bm = sp.diags([1 / 6, 4 / 6, 1 / 6], [-1, 0, 1], shape=(n, n), format="csc")
+    ref = fo.contour_estimate_eig(A, ct_o, Bm, X=X.copy())
+    got = fs.contour_estimate_eig(A, ct_g, Bm, X=X.copy(), solver_opts={"kind": _lib.SOLVER_KRYLOV, "inner_tol": 1e-11, "max_inner": 3000})
+    assert abs(got - ref) <= 1e-7 * max(1.0, abs(ref))
+
+
 # ------------------------------------------------------------------ errors / edge cases
 def test_dimension_errors(fs):
     with pytest.raises(ValueError, match="must be square"):
