@@ -326,6 +326,28 @@ def test_nlfeast_sparse_butterfly_matches_dense(fs, nep_fixtures, nlfeast_golden
         assert np.abs(exact - l).min() < 1e-10 * max(1.0, abs(l))
 
 
+def test_C4_reduced_butterfly_scaled(fs):
+    """C4 shape at reduced size: quartic butterfly with 24 x 24 one-dimensional blocks (n = 576, sparse
+    5-point coefficient patterns through the union-pattern kernels), 24 trapezoid nodes, m0 = 24."""
+    from feastsolver_jl_b200 import workloads as wl
+    mb, r, m0, nodes = 24, 0.12, 24, 24
+    coeffs = wl.butterfly_coeffs(mb)
+    T = fo.polynomial([a.toarray() for a in coeffs])
+    X0 = wl.rand_subspace(mb * mb, m0, seed=1)
+    lo, Xo, ro = fo.nlfeast(T, X0.copy(), nodes, 25, c=1 + 1j, r=r, eps=1e-11)
+    st = {}
+    lg, Xg, rg = fs.nlfeast(coeffs, X0.copy(), nodes, 25, c=1 + 1j, r=r, eps=1e-11, stats=st)
+    ino, ing = np.abs(lo - (1 + 1j)) <= r, np.abs(lg - (1 + 1j)) <= r
+    assert ing.sum() == ino.sum() == 17
+    match_eigs(lg[ing], lo[ino])
+    assert rg[ing].max() <= 10 * max(ro[ino].max(), 1e-13)
+    assert abs(len(st["history"]) - 4) <= 1     # the oracle converges in 4 passes
+    # residual definition: ||T(l) x|| / ||T(l)||_F with unit-norm x
+    j = int(np.flatnonzero(ing)[0])
+    Tl = T(lg[j])
+    assert abs(np.linalg.norm(Tl @ Xg[:, j]) / np.linalg.norm(Tl) - rg[j]) < 1e-13
+
+
 def test_nlfeast_linear_pencil_equals_feast(fs):
     n = 100
     A = np.diag(np.full(n, 2.0)) + np.diag(np.full(n - 1, -1.0), 1) + np.diag(np.full(n - 1, -1.0), -1)
