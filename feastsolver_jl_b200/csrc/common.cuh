@@ -118,6 +118,9 @@ struct feast_ctx {
     // contour
     std::vector<hc128> znodes, zweights;
     std::vector<int> owner;       // node -> rank
+    std::vector<double> node_cost; // measured device ms of the last solve of each node (all ranks, after the all-reduce)
+    bool have_costs = false;
+    int auto_balance = 1;         // re-shard nodes by measured cost before every contour pass (Krylov / store=0 only)
     // solver
     int solver = FEAST_SOLVER_AUTO, krylov = FEAST_KRYLOV_AUTO;
     double inner_tol = 1e-10;
