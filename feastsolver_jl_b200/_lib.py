@@ -74,6 +74,12 @@ SIGNATURES = {
     "feast_contour_apply": (_i, [_vp, _vp, _i, C.POINTER(FeastStats)]),
     "feast_beyn_reduce": (_i, [_vp, _vp, _vp]),
     "feast_orthonormalize_X": (_i, [_vp]),
+    "feast_dual_set_subspace": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _i64]),
+    "feast_dual_project": (_i, [_vp, _vp]),
+    "feast_dual_rotate": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "feast_dual_recover_residual": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "feast_dual_contour_apply": (_i, [_vp, _vp, C.POINTER(FeastStats)]),
+    "feast_dual_get": (_i, [_vp, _vp, _i64, _vp, _i64]),
     "feast_estimate_count": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(FeastStats)]),
     "feast_factorize": (_i, [_vp, _vp, _i, C.POINTER(_vp)]),
     "feast_solve": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _i64, _i]),

@@ -81,7 +81,7 @@ void free_problem_derived(feast_ctx* ctx) {
 }
 
 void free_blocks(feast_ctx* ctx) {
-    BlockVec* all[] = {&ctx->Q, &ctx->X, &ctx->R, &ctx->Q1, &ctx->W1, &ctx->W2, &ctx->kx, &ctx->kr,
+    BlockVec* all[] = {&ctx->Q, &ctx->X, &ctx->R, &ctx->Q1, &ctx->W1, &ctx->W2, &ctx->Ql, &ctx->Xl, &ctx->Rl, &ctx->kx, &ctx->kr,
                        &ctx->kp, &ctx->kq, &ctx->ks, &ctx->kt, &ctx->kv, &ctx->krh};
     for (auto* b : all) dev_free(b->p);
     dev_free(ctx->stage);
@@ -446,11 +446,35 @@ void rebalance_nodes(feast_ctx* ctx) {
     }
 }
 
+// W = op(slot)^H * V.  Dense: one DMMA GEMM on the conjugate-transposed view.  Sparse: supported when
+// the slot is (complex-)symmetric, op^H = conj(op): W = conj(op * conj(V)).
+int apply_slot_adjoint(feast_ctx* ctx, int slot, const c128* V, c128* W) {
+    const Operator& op = ctx->ops[slot];
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    if (op.kind == OP_IDENTITY) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(W, V, sizeof(c128) * n * m, cudaMemcpyDeviceToDevice, ctx->stream));
+        return 0;
+    }
+    if (op.kind == OP_DENSE)   // A^H(i,k) = conj(A(k,i)); dense slots are row-major
+        return launch_zgemm(ctx, (int)n, m, n, hc128(1, 0), op.dense, 1, n, true, V, m, 1, hc128(0, 0), W, m, 1);
+    if (op.kind == OP_CSR) {
+        if (!op.symmetric)
+            return feast_fail(ctx, FEAST_ERR_STATE, "adjoint of a non-symmetric sparse operator is not supported: pass it dense");
+        if (!op.is_complex) return apply_slot(ctx, slot, V, W);   // real symmetric: A^H = A
+        FEAST_TRY(ensure_block(ctx, ctx->W2));
+        FEAST_TRY(launch_conj(ctx, n * m, V, ctx->W2.p));
+        FEAST_TRY(apply_slot(ctx, slot, ctx->W2.p, W));
+        return launch_conj(ctx, n * m, W, W);
+    }
+    return feast_fail(ctx, FEAST_ERR_STATE, "operator slot %d is not set", slot);
+}
+
 // One shifted solve  (sum_i coef[i] slot_i) Y = rhs  with m0 right-hand sides: dense LU (stored per node
 // when store != 0, node index k >= 0) or Krylov on the union pattern.  `e1` is recorded between the
 // factorisation/assembly and the solve.  This is linsolve! (src/utils.jl:175-179) for one contour node.
 int solve_shifted(feast_ctx* ctx, int solver, int method, int k, const hc128* coef, const c128* rhs, c128* Y,
-                  feast_stats& st, cudaEvent_t e1, int* rc_final) {
+                  feast_stats& st, cudaEvent_t e1, int* rc_final, bool adjoint = false) {
     const int64_t n = ctx->n;
     const int m = ctx->m0;
     if (solver == FEAST_SOLVER_DENSE_LU) {
@@ -467,6 +491,7 @@ int solve_shifted(feast_ctx* ctx, int solver, int method, int k, const hc128* co
             scratch.lu = ctx->zdense; scratch.ipiv = ctx->zpiv; scratch.perm = ctx->zpiv + n; scratch.dinv = ctx->zdinv;
             f = &scratch;
         }
+        if (k == -2) need_factor = false;   // the scratch factorisation of the previous call is reused (adjoint solve)
         if (need_factor) {
             int info = 0;
             FEAST_TRY(factor_dense(ctx, coef, *f, &info));                                // feast.jl:36 / :65 lu
@@ -474,12 +499,22 @@ int solve_shifted(feast_ctx* ctx, int solver, int method, int k, const hc128* co
         }
         if (e1) cudaEventRecord(e1, ctx->stream);
         FEAST_TRY(ensure_block(ctx, ctx->W2));
-        FEAST_TRY(dense_getrs(ctx, n, f->lu, f->perm, f->dinv, m, rhs, Y, false));        // ldiv!
+        FEAST_TRY(dense_getrs(ctx, n, f->lu, f->perm, f->dinv, m, rhs, Y, adjoint));      // ldiv! (or F' \\ R)
     } else {
         FEAST_TRY(assemble_sparse_Z(ctx, coef, ctx->zvals));
         if (e1) cudaEventRecord(e1, ctx->stream);
         KrylovResult kr;
-        FEAST_TRY(krylov_solve(ctx, method, ctx->zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, &kr));
+        if (adjoint) {
+            // Z complex symmetric: Z^H = conj(Z), so Z^H y = b  <=>  Z conj(y) = conj(b)
+            if (!ctx->all_symmetric)
+                return feast_fail(ctx, FEAST_ERR_STATE, "adjoint Krylov solve needs symmetric operators: pass them dense");
+            FEAST_TRY(ensure_block(ctx, ctx->W2));
+            FEAST_TRY(launch_conj(ctx, n * m, rhs, ctx->W2.p));
+            FEAST_TRY(krylov_solve(ctx, method, ctx->zvals, ctx->W2.p, Y, ctx->inner_tol, ctx->max_inner, &kr));
+            FEAST_TRY(launch_conj(ctx, n * m, Y, Y));
+        } else {
+            FEAST_TRY(krylov_solve(ctx, method, ctx->zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, &kr));
+        }
         st.inner_iters_total += kr.iters;
         st.inner_iters_max = std::max(st.inner_iters_max, kr.iters);
         st.inner_relres_max = std::max(st.inner_relres_max, kr.relres_max);
@@ -1012,6 +1047,185 @@ int feast_estimate_count(feast_ctx* ctx, double* est, feast_stats* stats) {
     if (stats) *stats = st;
     if (st.info) return feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d of a shifted factorisation", st.info);
     return rc_final;
+}
+
+// ------------------------------------------------------------------------- two-sided driver (dual_gen_feast!)
+// src/feast.jl:165-257.  Right blocks live in Q/X/R, left blocks in Ql/Xl/Rl.  One LU per node serves both the
+// solve with A - zB and with its adjoint (the reference factors twice, feast.jl:185-194).
+int feast_dual_set_subspace(feast_ctx* ctx, int64_t n, int m0, const feast_c128* Xr, int64_t ldr, const feast_c128* Xl,
+                            int64_t ldl) {
+    FEAST_TRY(feast_set_subspace(ctx, n, m0, Xr, ldr));
+    ARG_CHECK(ctx, Xl != nullptr, 6, "null Xl");
+    ARG_CHECK(ctx, ldl >= n, 7, "ldl < n");
+    FEAST_TRY(ensure_block(ctx, ctx->Ql));
+    FEAST_TRY(ensure_block(ctx, ctx->Xl));
+    FEAST_TRY(ensure_block(ctx, ctx->Rl));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->stage, sizeof(c128) * n, Xl, sizeof(c128) * ldl, sizeof(c128) * n, m0,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    FEAST_TRY(launch_colmajor_to_rowmajor(ctx, n, m0, ctx->stage, n, ctx->Ql.p));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->Xl.p, ctx->Ql.p, sizeof(c128) * n * m0, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// G = Ql' B Qr   (feast.jl:199, the argument of svd!)
+int feast_dual_project(feast_ctx* ctx, feast_c128* G) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, G != nullptr, 2, "null G");
+    if (!ctx->Ql.p) return feast_fail(ctx, FEAST_ERR_STATE, "feast_dual_set_subspace has not been called");
+    if (ctx->problem == FEAST_PROBLEM_POLYNOMIAL) return feast_fail(ctx, FEAST_ERR_STATE, "linear problems only");
+    const int m = ctx->m0;
+    PhaseTimer tm(ctx, 0);
+    FEAST_TRY(ensure_block(ctx, ctx->W1));
+    FEAST_TRY(apply_slot(ctx, 1, ctx->Q.p, ctx->W1.p));
+    FEAST_TRY(launch_gram(ctx, ctx->n, m, ctx->Ql.p, ctx->W1.p, ctx->small_d));
+    CUDA_TRY(ctx, cudaMemcpyAsync(G, ctx->small_d, sizeof(c128) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
+    tm.stop();
+    return 0;
+}
+
+// Qr <- Qr Mr ; Ql <- Ql Ml (feast.jl:200-201) ; Aq = Ql' A Qr ; Bq = Ql' B Qr (feast.jl:202-205)
+int feast_dual_rotate(feast_ctx* ctx, const feast_c128* Mr, const feast_c128* Ml, feast_c128* Aq, feast_c128* Bq) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, Mr != nullptr, 2, "null Mr");
+    ARG_CHECK(ctx, Ml != nullptr, 3, "null Ml");
+    ARG_CHECK(ctx, Aq != nullptr, 4, "null Aq");
+    ARG_CHECK(ctx, Bq != nullptr, 5, "null Bq");
+    if (!ctx->Ql.p) return feast_fail(ctx, FEAST_ERR_STATE, "feast_dual_set_subspace has not been called");
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    PhaseTimer tm(ctx, 0);
+    FEAST_TRY(ensure_block(ctx, ctx->W1));
+    c128* M_d = ctx->small_d;
+    c128* G_d = ctx->small_d + (size_t)m * m;
+    CUDA_TRY(ctx, cudaMemcpyAsync(M_d, Mr, sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
+    FEAST_TRY(launch_update(ctx, n, m, ctx->Q.p, M_d, ctx->W1.p));
+    std::swap(ctx->Q.p, ctx->W1.p);
+    CUDA_TRY(ctx, cudaMemcpyAsync(M_d, Ml, sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
+    FEAST_TRY(launch_update(ctx, n, m, ctx->Ql.p, M_d, ctx->W1.p));
+    std::swap(ctx->Ql.p, ctx->W1.p);
+    FEAST_TRY(apply_slot(ctx, 0, ctx->Q.p, ctx->R.p));
+    FEAST_TRY(launch_gram(ctx, n, m, ctx->Ql.p, ctx->R.p, G_d));
+    CUDA_TRY(ctx, cudaMemcpyAsync(Aq, G_d, sizeof(c128) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
+    FEAST_TRY(apply_slot(ctx, 1, ctx->Q.p, ctx->W1.p));
+    FEAST_TRY(launch_gram(ctx, n, m, ctx->Ql.p, ctx->W1.p, G_d));
+    CUDA_TRY(ctx, cudaMemcpyAsync(Bq, G_d, sizeof(c128) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
+    tm.stop();
+    return 0;
+}
+
+// Xr = Qr Xqr, Xl = Ql Xql (feast.jl:209,212); update_R! on both sides (feast.jl:213-214, the left one with
+// conj(lambda), see the oracle docstring); resr_j = ||Rr_j|| (feast.jl:215)
+int feast_dual_recover_residual(feast_ctx* ctx, const feast_c128* Xqr, const feast_c128* Xql, const feast_c128* lambda,
+                                double* resr) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, Xqr != nullptr, 2, "null Xqr");
+    ARG_CHECK(ctx, Xql != nullptr, 3, "null Xql");
+    ARG_CHECK(ctx, lambda != nullptr, 4, "null lambda");
+    ARG_CHECK(ctx, resr != nullptr, 5, "null resr");
+    if (!ctx->Ql.p) return feast_fail(ctx, FEAST_ERR_STATE, "feast_dual_set_subspace has not been called");
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    PhaseTimer tm(ctx, 1);
+    FEAST_TRY(ensure_block(ctx, ctx->W1));
+    c128* M_d = ctx->small_d;
+    c128* lam_d = ctx->small_d + (size_t)2 * m * m;
+    c128* lamc_d = lam_d + m;
+    double* nrm_d = (double*)(ctx->small_d + (size_t)3 * m * m);
+    std::vector<hc128> lamc(m);
+    for (int j = 0; j < m; ++j) lamc[j] = hc128(lambda[j].re, -lambda[j].im);
+    CUDA_TRY(ctx, cudaMemcpyAsync(lam_d, lambda, sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(lamc_d, lamc.data(), sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
+    // right side
+    CUDA_TRY(ctx, cudaMemcpyAsync(M_d, Xqr, sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
+    FEAST_TRY(launch_update(ctx, n, m, ctx->Q.p, M_d, ctx->X.p));
+    FEAST_TRY(launch_colnorm2(ctx, n, m, ctx->X.p, nrm_d));
+    FEAST_TRY(launch_colnormalize(ctx, n, m, ctx->X.p, nrm_d));
+    FEAST_TRY(apply_slot(ctx, 0, ctx->X.p, ctx->R.p));
+    FEAST_TRY(apply_slot(ctx, 1, ctx->X.p, ctx->W1.p));
+    FEAST_TRY(launch_residual_combine(ctx, n, m, ctx->R.p, ctx->W1.p, lam_d));
+    FEAST_TRY(launch_colnorm2(ctx, n, m, ctx->R.p, nrm_d));
+    double* hres = (double*)ctx->pinned;
+    CUDA_TRY(ctx, cudaMemcpyAsync(hres, nrm_d, sizeof(double) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    // left side
+    CUDA_TRY(ctx, cudaMemcpyAsync(M_d, Xql, sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
+    FEAST_TRY(launch_update(ctx, n, m, ctx->Ql.p, M_d, ctx->Xl.p));
+    FEAST_TRY(launch_colnorm2(ctx, n, m, ctx->Xl.p, nrm_d));
+    FEAST_TRY(launch_colnormalize(ctx, n, m, ctx->Xl.p, nrm_d));
+    FEAST_TRY(apply_slot_adjoint(ctx, 0, ctx->Xl.p, ctx->Rl.p));
+    FEAST_TRY(apply_slot_adjoint(ctx, 1, ctx->Xl.p, ctx->W1.p));
+    FEAST_TRY(launch_residual_combine(ctx, n, m, ctx->Rl.p, ctx->W1.p, lamc_d));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int j = 0; j < m; ++j) resr[j] = std::sqrt(hres[j]);
+    tm.stop();
+    return 0;
+}
+
+// Qr = sum_k (Xr - (A - z_k B)^-1 Rr) diag(w_k/(z_k - l)) ; Ql = sum_k (Xl - (A - z_k B)^-H Rl) diag(conj(w_k/(z_k - l)))
+// (feast.jl:225-247), node-sharded, both accumulators all-reduced.
+int feast_dual_contour_apply(feast_ctx* ctx, const feast_c128* lambda, feast_stats* stats) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, lambda != nullptr, 2, "null lambda");
+    if (!ctx->Ql.p) return feast_fail(ctx, FEAST_ERR_STATE, "feast_dual_set_subspace has not been called");
+    if (ctx->znodes.empty()) return feast_fail(ctx, FEAST_ERR_STATE, "feast_set_contour has not been called");
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    const int solver = effective_solver(ctx), method = effective_krylov(ctx);
+    if (solver == FEAST_SOLVER_KRYLOV && ctx->storage_dense)
+        return feast_fail(ctx, FEAST_ERR_STATE, "Krylov inner solves need sparse operators");
+    FEAST_TRY(ensure_block(ctx, ctx->W1));
+    FEAST_TRY(ensure_block(ctx, ctx->W2));
+    if (solver == FEAST_SOLVER_KRYLOV) FEAST_TRY(ensure_krylov_work(ctx, method));
+    feast_stats st;
+    memset(&st, 0, sizeof(st));
+    PhaseTimer tm(ctx, 2);
+    int rc_final = 0;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->Q.p, 0, sizeof(c128) * n * m, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->Ql.p, 0, sizeof(c128) * n * m, ctx->stream));
+    const int nnodes = (int)ctx->znodes.size();
+    if (ctx->store && (int)ctx->stored.size() != nnodes) ctx->stored.resize(nnodes);
+    c128* d_d = ctx->small_d + (size_t)3 * m * m;
+    c128* dl_d = d_d + m;
+    std::vector<hc128> d(m), dl(m);
+    hc128 coef[FEAST_MAX_SLOTS];
+    for (int k = 0; k < nnodes; ++k) {
+        if (ctx->owner[k] != ctx->rank) continue;
+        st.nodes_local++;
+        const hc128 z = ctx->znodes[k], w = ctx->zweights[k];
+        node_coefs(ctx, z, coef);
+        for (int j = 0; j < m; ++j) {
+            d[j] = w / (z - hc128(lambda[j].re, lambda[j].im));   // feast.jl:227,233
+            dl[j] = std::conj(d[j]);                               // feast.jl:236,245
+        }
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_d, d.data(), sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(dl_d, dl.data(), sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
+        FEAST_TRY(solve_shifted(ctx, solver, method, k, coef, ctx->R.p, ctx->W1.p, st, nullptr, &rc_final, false));
+        FEAST_TRY(launch_accumulate(ctx, n, m, ctx->X.p, ctx->W1.p, d_d, ctx->Q.p, nullptr, z, false));
+        FEAST_TRY(solve_shifted(ctx, solver, method, ctx->store ? k : -2, coef, ctx->Rl.p, ctx->W1.p, st, nullptr, &rc_final, true));
+        FEAST_TRY(launch_accumulate(ctx, n, m, ctx->Xl.p, ctx->W1.p, dl_d, ctx->Ql.p, nullptr, z, false));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (ctx->nranks > 1) {
+        const NcclApi* api = nccl_api();
+        int rc = api->AllReduce(ctx->Q.p, ctx->Q.p, (size_t)2 * n * m, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
+        if (!rc) rc = api->AllReduce(ctx->Ql.p, ctx->Ql.p, (size_t)2 * n * m, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
+        if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclAllReduce failed");
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    st.t_total_ms = tm.stop();
+    if (stats) *stats = st;
+    if (st.info) return feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d of a shifted factorisation", st.info);
+    return rc_final;
+}
+
+int feast_dual_get(feast_ctx* ctx, feast_c128* Xr, int64_t ldr, feast_c128* Xl, int64_t ldl) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, Xr != nullptr, 2, "null Xr");
+    ARG_CHECK(ctx, ldr >= ctx->n, 3, "ldr < n");
+    ARG_CHECK(ctx, Xl != nullptr, 4, "null Xl");
+    ARG_CHECK(ctx, ldl >= ctx->n, 5, "ldl < n");
+    FEAST_TRY(download_block(ctx, ctx->X, Xr, ldr));
+    return download_block(ctx, ctx->Xl, Xl, ldl);
 }
 
 int feast_orthonormalize_X(feast_ctx* ctx) {

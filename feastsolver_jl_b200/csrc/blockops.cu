@@ -81,6 +81,12 @@ __global__ void accumulate_kernel(int64_t total, int m, const c128* __restrict__
         if (Q1) Q1[t] = cadd(Q1[t], cmul(z, term));
     }
 }
+__global__ void conj_kernel(int64_t count, const c128* __restrict__ s, c128* __restrict__ d) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        const c128 v = s[t];
+        d[t] = cmake(v.x, -v.y);
+    }
+}
 __global__ void real_to_complex_kernel(int64_t count, const double* __restrict__ s, c128* __restrict__ d) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x)
         d[t] = cmake(s[t], 0.0);
@@ -241,6 +247,11 @@ int launch_colmajor_to_rowmajor(feast_ctx* ctx, int64_t n, int m, const c128* sr
 int launch_rowmajor_to_colmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, c128* dst, int64_t ld) {
     dim3 grid(ceil_div(n, 32), ceil_div(m, 32)), block(32, 8);
     transpose_kernel<false><<<grid, block, 0, ctx->stream>>>(n, m, src, dst, ld);
+    KLAUNCH_CHECK(ctx);
+    return 0;
+}
+int launch_conj(feast_ctx* ctx, int64_t count, const c128* src, c128* dst) {
+    conj_kernel<<<ew_grid(count), 256, 0, ctx->stream>>>(count, src, dst);
     KLAUNCH_CHECK(ctx);
     return 0;
 }

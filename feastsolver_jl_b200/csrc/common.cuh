@@ -134,6 +134,7 @@ struct feast_ctx {
     // subspace blocks
     int m0 = 0;
     BlockVec Q, X, R, Q1, W1, W2;       // Q1: second moment accumulator (polynomial)
+    BlockVec Ql, Xl, Rl;                // left subspace of the two-sided driver (dual_gen_feast!)
     BlockVec kx, kr, kp, kq, ks, kt, kv, krh; // Krylov work
     c128* gm_V = nullptr;         // GMRES basis: (gm_restart + 1) blocks
     void* gm_small = nullptr;     // GMRES per-column Hessenberg / rotations

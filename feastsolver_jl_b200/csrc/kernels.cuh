@@ -46,6 +46,7 @@ int launch_accumulate(feast_ctx* ctx, int64_t n, int m, const c128* X, const c12
 int launch_colmajor_to_rowmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, int64_t ld, c128* dst);
 int launch_rowmajor_to_colmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, c128* dst, int64_t ld);
 int launch_real_to_complex(feast_ctx* ctx, int64_t count, const double* src, c128* dst);
+int launch_conj(feast_ctx* ctx, int64_t count, const c128* src, c128* dst);  // dst = conj(src), may alias
 // Z(n x n) = sum_i coef[i] * D_i (dense col-major slots; identity slots add coef to the diagonal)
 int launch_assemble_dense(feast_ctx* ctx, int64_t n, int nslots, const c128* const* D, const int* kinds,
                           const hc128* coef, c128* Z);

@@ -182,6 +182,47 @@ class FeastContext:
         self.last_stats = st.as_dict()
         return float(est.value)
 
+    # -- two-sided driver
+    def dual_set_subspace(self, Xr, Xl):
+        Xr, Xl = _lib.as_f_c128(Xr), _lib.as_f_c128(Xl)
+        n, m0 = Xr.shape
+        self._ck(self.lib.feast_dual_set_subspace(self.h, n, m0, _lib.ptr(Xr), n, _lib.ptr(Xl), n))
+        self.m0 = m0
+
+    def dual_project(self):
+        G = np.empty((self.m0, self.m0), np.complex128, order="F")
+        self._ck(self.lib.feast_dual_project(self.h, _lib.ptr(G)))
+        return G
+
+    def dual_rotate(self, Mr, Ml):
+        m = self.m0
+        Mr, Ml = np.asfortranarray(Mr, dtype=np.complex128), np.asfortranarray(Ml, dtype=np.complex128)
+        Aq = np.empty((m, m), np.complex128, order="F")
+        Bq = np.empty((m, m), np.complex128, order="F")
+        self._ck(self.lib.feast_dual_rotate(self.h, _lib.ptr(Mr), _lib.ptr(Ml), _lib.ptr(Aq), _lib.ptr(Bq)))
+        return Aq, Bq
+
+    def dual_recover_residual(self, Xqr, Xql, lam):
+        Xqr, Xql = np.asfortranarray(Xqr, dtype=np.complex128), np.asfortranarray(Xql, dtype=np.complex128)
+        lam = np.ascontiguousarray(lam, dtype=np.complex128)
+        res = np.empty(self.m0, np.float64)
+        self._ck(self.lib.feast_dual_recover_residual(self.h, _lib.ptr(Xqr), _lib.ptr(Xql), _lib.ptr(lam), _lib.ptr(res)))
+        return res
+
+    def dual_contour_apply(self, lam):
+        st = FeastStats()
+        lam = np.ascontiguousarray(lam, dtype=np.complex128)
+        rc = self.lib.feast_dual_contour_apply(self.h, _lib.ptr(lam), C.byref(st))
+        self._ck(rc, allow=(0, _lib.FEAST_WARN_INNER_MAXIT))
+        self.last_stats = st.as_dict()
+        return self.last_stats
+
+    def dual_get(self):
+        Xr = np.empty((self.n, self.m0), np.complex128, order="F")
+        Xl = np.empty((self.n, self.m0), np.complex128, order="F")
+        self._ck(self.lib.feast_dual_get(self.h, _lib.ptr(Xr), self.n, _lib.ptr(Xl), self.n))
+        return Xr, Xl
+
     def orthonormalize_X(self):
         self._ck(self.lib.feast_orthonormalize_X(self.h))
 
@@ -460,3 +501,79 @@ def contour_estimate_eig(A, contour, B=I, *, samples=None, eps=1e-12, debug=Fals
     finally:
         if own_ctx:
             ctx.close()
+
+
+def dual_gen_feast(Xr, Xl, A, B, contour: Contour | None = None, *, nodes=8, iter=10, c=complex(0.0, 0.0), r=1.0,
+                   debug=False, store=False, eps=1e-12, factorizer=None, left_divider=None,
+                   ctx=None, solver_opts=None, stats=None, comm=None):
+    """dual_gen_feast!(Xr, Xl, A, B[, contour]; ...)  (src/feast.jl:158-257): two-sided FEAST for
+    non-Hermitian pencils; returns (L[in], Xr[:, in], Xl[:, in], resr[in]).  `B` may be `I`.
+
+    Restates the INTENDED semantics where upstream has defects (both documented in the oracle):
+    `Diagonal(1.0/S.S)` (feast.jl:200-201) is taken as the elementwise Sigma^-1/2 on both sides (so that
+    Ql' B Qr = I, the intent stated at feast.jl:205), and the left residual uses conj(lambda) (feast.jl:214).  The m0 x m0 SVD and the two reduced eigenproblems run on host
+    LAPACK; everything n-sized runs in libfeast_cuda.so with ONE LU per node serving A - zB and its
+    adjoint."""
+    _check_plugins(factorizer, left_divider, False)
+    if contour is None:
+        contour = circular_contour_trapezoidal(c, r, nodes)  # feast.jl:163
+        store = False                                         # the wrapper drops `store` (feast.jl:164)
+    N, m0 = Xl.shape
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("Incorrect dimensions of A, must be square")
+    if A.shape[0] != N:
+        raise ValueError("Incorrect dimensions of X, must match A")
+    own_ctx = ctx is None
+    if own_ctx:
+        ctx = FeastContext()
+    try:
+        if B is None or isinstance(B, str):
+            Bop = None
+        else:
+            A, Bop = _densify_if_mixed(A, B)
+        ctx.set_operator(0, A)
+        ctx.set_operator(1, Bop, n=N)
+        ctx.set_problem(_lib.PROBLEM_GENERALIZED, 2, N)
+        if comm is not None:
+            comm(ctx)
+        ctx.set_contour(contour.nodes, contour.weights)
+        if ctx.nranks > 1:
+            ctx.set_node_owners(node_owners(contour.nodes, ctx.nranks))
+        ctx.set_solver(store=store, **(solver_opts or {}))
+        ctx.dual_set_subspace(Xr, Xl)
+        Lam = np.zeros(m0, complex)
+        resr = np.zeros(m0)
+        hist = []
+        for nit in range(iter + 1):
+            G = ctx.dual_project()                                   # Ql' B Qr                feast.jl:199
+            U, S, Vh = sla.svd(G, check_finite=False)                # host m0 x m0 SVD
+            sc = 1.0 / np.sqrt(np.maximum(S, S[0] * 1e-280))         # Sigma^-1/2 on both sides: Ql' B Qr = I
+            Aq, Bq = ctx.dual_rotate(Vh.conj().T * sc[None, :], U * sc[None, :])   # feast.jl:200-205
+            Lam, Xq = _eig_sorted(Aq, Bq)                            # feast.jl:206-208
+            wl, vl = sla.eig(Aq.conj().T, Bq.conj().T, check_finite=False)   # feast.jl:210-211
+            order = [int(np.argmin(np.abs(wl - np.conj(l)))) for l in Lam]   # pair left vectors with Lam
+            resr = ctx.dual_recover_residual(Xq, vl[:, order], Lam)  # feast.jl:209-215
+            inside = in_contour(Lam, contour)
+            if debug:
+                iter_debug_print(nit, Lam, resr, contour, 1e-5)
+            rec = {"nit": nit, "inside": int(inside.sum()),
+                   "max_res_inside": float(resr[inside].max()) if inside.any() else float("nan")}
+            if inside.any() and resr[inside].max() < eps:            # feast.jl:218
+                hist.append(rec)
+                break
+            if nit < iter:
+                rec.update(ctx.dual_contour_apply(Lam))              # feast.jl:222-248
+            hist.append(rec)
+        xr, xl = ctx.dual_get()
+        Xr[:, :] = xr
+        Xl[:, :] = xl
+        if stats is not None:
+            stats["history"] = hist
+            stats["launches"] = ctx.launch_count()
+    finally:
+        if own_ctx:
+            ctx.close()
+    inside = in_contour(Lam, contour)
+    if not inside.any():
+        print("no eigenvalues found in contour!")
+    return Lam[inside], Xr[:, inside], Xl[:, inside], resr[inside]

@@ -152,6 +152,19 @@ FEAST_API int  feast_beyn_reduce(feast_ctx* ctx, feast_c128* Rf, feast_c128* G1)
 /* contour_estimate_eig (src/stochastic.jl:2-33): with the probe vectors uploaded by
  * feast_set_subspace, est = Re sum_k w_k tr(X' (z_k B - A)^-1 X) / m0 (node-sharded).   */
 FEAST_API int  feast_estimate_count(feast_ctx* ctx, double* est, feast_stats* stats);
+/* ---- two-sided driver dual_gen_feast! (src/feast.jl:165-257) -------------------------
+ * Right blocks are the ones of the one-sided path; left blocks Ql/Xl/Rl are added.  The m0 x m0
+ * SVD bi-orthogonalisation (feast.jl:199-201) and the two reduced eigenproblems (:206,:210) stay
+ * on the host.  One LU per node serves A - zB and its adjoint (getrs 'C').                 */
+FEAST_API int  feast_dual_set_subspace(feast_ctx* ctx, int64_t n, int m0, const feast_c128* Xr, int64_t ldr,
+                             const feast_c128* Xl, int64_t ldl);
+FEAST_API int  feast_dual_project(feast_ctx* ctx, feast_c128* G);            /* G = Ql' B Qr          feast.jl:199     */
+FEAST_API int  feast_dual_rotate(feast_ctx* ctx, const feast_c128* Mr, const feast_c128* Ml,
+                       feast_c128* Aq, feast_c128* Bq);                /* feast.jl:200-205                       */
+FEAST_API int  feast_dual_recover_residual(feast_ctx* ctx, const feast_c128* Xqr, const feast_c128* Xql,
+                                 const feast_c128* lambda, double* resr);  /* feast.jl:207-215                  */
+FEAST_API int  feast_dual_contour_apply(feast_ctx* ctx, const feast_c128* lambda, feast_stats* stats); /* :225-247 */
+FEAST_API int  feast_dual_get(feast_ctx* ctx, feast_c128* Xr, int64_t ldr, feast_c128* Xl, int64_t ldl);
 /* nlfeast! first statement: X <- thin Q of X (src/nlfeast.jl:12-13).           */
 FEAST_API int  feast_orthonormalize_X(feast_ctx* ctx);
 

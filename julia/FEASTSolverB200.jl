@@ -13,7 +13,7 @@ module FEASTSolverB200
 using LinearAlgebra
 using SparseArrays
 
-export feast!, gen_feast!, nlfeast!
+export feast!, gen_feast!, dual_gen_feast!, nlfeast!, contour_estimate_eig
 export in_contour, circular_contour_trapezoidal, circular_contour_gauss,
        rectangular_contour_gauss, rectangular_contour_trapezoidal, rational_func
 export Contour, CircularContour, RectangularContour, CustomContour
@@ -181,6 +181,76 @@ function gen_feast!(X::AbstractMatrix, A::AbstractMatrix, B::AbstractMatrix, con
                     store=false, ϵ=1e-12, factorizer=lu, left_divider=ldiv!)
     _check_plugins(factorizer, left_divider, false)
     _linear!(X, A, B, contour, iter, ϵ, debug, store, true)
+end
+
+# ---------------------------------------------------------------- two-sided driver (src/feast.jl:158-257)
+function dual_gen_feast!(Xr::AbstractMatrix, Xl::AbstractMatrix, A::AbstractMatrix, B; nodes::Integer=8, iter::Integer=10,
+                         c=complex(0.0, 0.0), r=1.0, debug=false, store=false, ϵ=1e-12, factorizer=lu, left_divider=ldiv!)
+    dual_gen_feast!(Xr, Xl, A, B, circular_contour_trapezoidal(c, r, nodes); iter=iter, debug=debug, ϵ=ϵ, factorizer=factorizer, left_divider=ldiv!)
+end
+function dual_gen_feast!(Xr::AbstractMatrix, Xl::AbstractMatrix, A::AbstractMatrix, B, contour::Contour; iter::Integer=10,
+                         debug=false, store=false, ϵ=1e-12, factorizer=lu, left_divider=ldiv!)
+    _check_plugins(factorizer, left_divider, false)
+    N, m₀ = size(Xl)
+    size(A, 1) != size(A, 2) && error("Incorrect dimensions of A, must be square")
+    size(A, 1) != N && error("Incorrect dimensions of X, must match A")
+    ctx = FeastCtx()
+    _set_operator!(ctx, 0, A, N); _set_operator!(ctx, 1, B, N)
+    _ck(ctx, ccall((:feast_set_problem, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint), ctx.h, 1, 2))
+    z = convert(Vector{ComplexF64}, contour.nodes); w = convert(Vector{ComplexF64}, contour.weights)
+    _ck(ctx, ccall((:feast_set_contour, libfeast), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}), ctx.h, length(z), z, w))
+    _ck(ctx, ccall((:feast_set_solver, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cint, Cint), ctx.h, 0, 0, 1e-8, 4000, store))
+    Xrc, Xlc = convert(Matrix{ComplexF64}, Xr), convert(Matrix{ComplexF64}, Xl)
+    _ck(ctx, ccall((:feast_dual_set_subspace, libfeast), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{ComplexF64}, Int64, Ptr{ComplexF64}, Int64),
+                   ctx.h, N, m₀, Xrc, N, Xlc, N))
+    Λ, resr = zeros(ComplexF64, m₀), zeros(m₀)
+    G, Aq, Bq = zeros(ComplexF64, m₀, m₀), zeros(ComplexF64, m₀, m₀), zeros(ComplexF64, m₀, m₀)
+    for nit = 0:iter
+        _ck(ctx, ccall((:feast_dual_project, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}), ctx.h, G))          # feast.jl:199
+        S = svd!(copy(G))
+        sc = Diagonal(1.0 ./ sqrt.(S.S))                       # intended elementwise scaling (feast.jl:200-201,205)
+        Mr = convert(Matrix{ComplexF64}, S.V * sc); Ml = convert(Matrix{ComplexF64}, S.U * sc)
+        _ck(ctx, ccall((:feast_dual_rotate, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}),
+                       ctx.h, Mr, Ml, Aq, Bq))
+        F = eigen(Aq, Bq); Λ .= F.values                                                                        # feast.jl:206
+        Fl = eigen(Matrix(Aq'), Matrix(Bq'))                                                                     # feast.jl:210
+        p = [argmin(abs.(Fl.values .- conj(l))) for l in Λ]
+        Xqr = convert(Matrix{ComplexF64}, F.vectors); Xql = convert(Matrix{ComplexF64}, Fl.vectors[:, p])
+        _ck(ctx, ccall((:feast_dual_recover_residual, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Cdouble}),
+                       ctx.h, Xqr, Xql, Λ, resr))
+        contour_nonempty = reduce(|, in_contour(Λ, contour))
+        if contour_nonempty && maximum(resr[in_contour(Λ, contour)]) < ϵ
+            break
+        end
+        if nit < iter
+            _ck(ctx, ccall((:feast_dual_contour_apply, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{Cvoid}), ctx.h, Λ, C_NULL); allow=(0, 2000))
+        end
+    end
+    _ck(ctx, ccall((:feast_dual_get, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Int64, Ptr{ComplexF64}, Int64), ctx.h, Xrc, N, Xlc, N))
+    Xr .= Xrc; Xl .= Xlc
+    finalize(ctx)
+    inside = in_contour(Λ, contour)
+    !reduce(|, inside) && println("no eigenvalues found in contour!")
+    Λ[inside], Xr[:, inside], Xl[:, inside], resr[inside]
+end
+
+# ---------------------------------------------------------------- stochastic count estimate (src/stochastic.jl:2-33)
+function contour_estimate_eig(A::AbstractMatrix, contour::Contour, B=I; samples::Integer=min(100, size(A, 1)), ϵ=1e-12,
+                              debug=false, mixed_prec=false, factorizer=lu, left_divider=ldiv!)
+    _check_plugins(factorizer, left_divider, mixed_prec)
+    N = size(A, 1)
+    X = randn(ComplexF64, N, samples)
+    ctx = FeastCtx()
+    _set_operator!(ctx, 0, A, N)
+    B isa UniformScaling || _set_operator!(ctx, 1, B, N)
+    _ck(ctx, ccall((:feast_set_problem, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint), ctx.h, B isa UniformScaling ? 0 : 1, B isa UniformScaling ? 1 : 2))
+    z = convert(Vector{ComplexF64}, contour.nodes); w = convert(Vector{ComplexF64}, contour.weights)
+    _ck(ctx, ccall((:feast_set_contour, libfeast), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}), ctx.h, length(z), z, w))
+    _ck(ctx, ccall((:feast_set_subspace, libfeast), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{ComplexF64}, Int64), ctx.h, N, samples, X, N))
+    est = Ref{Cdouble}(0.0)
+    _ck(ctx, ccall((:feast_estimate_count, libfeast), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ptr{Cvoid}), ctx.h, est, C_NULL); allow=(0, 2000))
+    finalize(ctx)
+    est[]
 end
 
 # ---------------------------------------------------------------- nonlinear driver (added method: coefficients)

@@ -366,10 +366,13 @@ def dual_gen_feast(Xr, Xl, A, B, contour=None, *, nodes=8, iter=10, c=0.0 + 0.0j
     Two upstream defects are restated with their INTENDED semantics (the only
     upstream call with an assertion is commented out, test/runtests.jl:24-26, so
     this routine is PARITY UNPINNED):
-      * `Diagonal(1.0/S.S)` (feast.jl:200-201) is Number/Vector in Julia, not the
-        elementwise inverse; here both bases are scaled by the elementwise
-        Sigma^-1.  The reduced pencil (Aq, Bq) is formed explicitly, so any
-        nonsingular scaling gives the same Ritz values.
+      * `Diagonal(1.0/S.S)` (feast.jl:200-201) is Number/Vector in Julia, not an
+        elementwise inverse.  The comment at feast.jl:205 ("Bq = Q' * Q = I") shows
+        the intent: bi-orthonormalise so that Ql' B Qr = I, i.e. scale BOTH bases
+        by the elementwise Sigma^-1/2 (Sigma^-1 on both sides would give Sigma^-1
+        and overflows once the surplus directions have been filtered away).  The
+        reduced pencil (Aq, Bq) is formed explicitly, so any nonsingular scaling
+        gives the same Ritz values.
       * `update_R!(Xl, Rl, L, A', B')` (feast.jl:214) uses L where a left
         eigenpair satisfies A'y = conj(l) B'y; the conj resolvent at feast.jl:238
         is only consistent with R_l = (A' - conj(l) B') y, which is what is used.
@@ -400,8 +403,9 @@ def dual_gen_feast(Xr, Xl, A, B, contour=None, *, nodes=8, iter=10, c=0.0 + 0.0j
     for nit in range(iter + 1):
         nit_done = nit
         U, S, Vh = sla.svd(Ql.conj().T @ (Bop @ Qr))  # feast.jl:199
-        Qr = Qr @ Vh.conj().T * (1.0 / S)[None, :]
-        Ql = Ql @ U * (1.0 / S)[None, :]
+        sc = 1.0 / np.sqrt(np.maximum(S, S[0] * 1e-280))  # Sigma^-1/2 on both sides: Ql' B Qr = I (feast.jl:205 comment)
+        Qr = Qr @ Vh.conj().T * sc[None, :]
+        Ql = Ql @ U * sc[None, :]
         Aq = Ql.conj().T @ (Ac @ Qr)
         Bq = Ql.conj().T @ (Bop @ Qr)
         w, v = sla.eig(Aq, Bq)  # feast.jl:206

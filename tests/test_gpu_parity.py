@@ -425,6 +425,52 @@ def test_contour_estimate_eig_matches_oracle(fs):
     assert abs(got - ref) <= 1e-7 * max(1.0, abs(ref))
 
 
+def test_dual_gen_feast_dense_nonhermitian(fs):
+    """Two-sided driver (src/feast.jl:165-257) on a mildly non-normal dense matrix, B = I
+    (test/non_hermitian.jl:27 calls it with `I`), store=true and store=false, against the oracle."""
+    N = 60
+    rng = np.random.default_rng(3)
+    D = np.diag(np.linspace(0.0, 6.0, N) + 0.3j * rng.standard_normal(N))
+    V = np.eye(N) + 0.05 * (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N)))
+    A = V @ D @ np.linalg.inv(V)
+    C, R = 1.0 + 0.0j, 0.8
+    Xr0, Xl0 = x0(N, 24, 7), x0(N, 24, 8)
+    eo, vro, vlo, ro = fo.dual_gen_feast(Xr0.copy(), Xl0.copy(), A, None, fo.circular_contour_trapezoidal(C, R, 16), iter=20, eps=1e-10)
+    ex = np.diag(D)
+    ex = ex[np.abs(ex - C) <= R]
+    for store in (False, True):
+        eg, vr, vl, rg = fs.dual_gen_feast(Xr0.copy(), Xl0.copy(), A, fs.I, fs.circular_contour_trapezoidal(C, R, 16),
+                                           iter=20, eps=1e-10, store=store)
+        assert eg.size == eo.size == ex.size
+        match_eigs(eg, eo, rtol=1e-9)
+        match_eigs(eg, ex, rtol=1e-9)
+        assert rg.max() <= 10 * max(ro.max(), 1e-12)
+        # right and left eigenvectors: A v = l v and w' A = l w'
+        for j in range(eg.size):
+            assert np.linalg.norm(A @ vr[:, j] - eg[j] * vr[:, j]) < 1e-8
+            assert np.linalg.norm(A.conj().T @ vl[:, j] - np.conj(eg[j]) * vl[:, j]) < 1e-6
+
+
+def test_dual_gen_feast_sparse_symmetric_pencil(fs):
+    """Sparse generalized pencil through the Krylov path: the adjoint solve of a complex-symmetric
+    shifted operator is conj(COCG(conj(b)))."""
+    from feastsolver_jl_b200 import workloads as wl
+    from feastsolver_jl_b200 import _lib
+    m = 10
+    A, B = wl.laplacian3d_pencil(m)
+    c, r, cnt = wl.c2_slice(m, target=10)
+    Xr0, Xl0 = wl.rand_subspace(m ** 3, 20, seed=0), wl.rand_subspace(m ** 3, 20, seed=1)
+    eo, vro, vlo, ro = fo.dual_gen_feast(Xr0.copy(), Xl0.copy(), A, B, fo.circular_contour_gauss(c, r, 16), iter=12, eps=1e-11)
+    eg, vr, vl, rg = fs.dual_gen_feast(Xr0.copy(), Xl0.copy(), A, B, fs.circular_contour_gauss(c, r, 16), iter=12, eps=1e-11,
+                                       solver_opts={"kind": _lib.SOLVER_KRYLOV, "inner_tol": 1e-11})
+    exact = wl.laplacian3d_spectrum(m)
+    exact = exact[np.abs(exact - c) <= r]
+    assert eg.size == eo.size == cnt == exact.size
+    match_eigs(eg, eo, rtol=1e-8)
+    match_eigs(eg, exact.astype(complex), rtol=1e-8)
+    assert rg.max() <= 10 * max(ro.max(), 1e-12)
+
+
 # ------------------------------------------------------------------ errors / edge cases
 def test_dimension_errors(fs):
     with pytest.raises(ValueError, match="must be square"):
