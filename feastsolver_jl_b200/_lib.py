@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfeast_cuda.so")
 FEAST_OK = 0
 FEAST_ERR_CUDA, FEAST_ERR_NCCL, FEAST_ERR_OOM, FEAST_ERR_STATE, FEAST_ERR_SINGULAR = 1000, 1001, 1002, 1003, 1004
 FEAST_WARN_INNER_MAXIT = 2000
-SOLVER_AUTO, SOLVER_DENSE_LU, SOLVER_KRYLOV = 0, 1, 2
+SOLVER_AUTO, SOLVER_DENSE_LU, SOLVER_KRYLOV, SOLVER_BANDED_LU = 0, 1, 2, 3
 KRYLOV_AUTO, KRYLOV_COCG, KRYLOV_BICGSTAB, KRYLOV_GMRES = 0, 1, 2, 3
 PROBLEM_STANDARD, PROBLEM_GENERALIZED, PROBLEM_POLYNOMIAL = 0, 1, 2
 MAX_SLOTS = 8

@@ -76,6 +76,11 @@ void free_problem_derived(feast_ctx* ctx) {
     dev_free(ctx->zdinv);
     for (auto& f : ctx->stored) { dev_free(f.lu); dev_free(f.ipiv); dev_free(f.perm); dev_free(f.dinv); }
     ctx->stored.clear();
+    for (auto& f : ctx->bstored) band_free(f);
+    ctx->bstored.clear();
+    band_free(ctx->bscratch);
+    dev_free(ctx->band_tmp);
+    ctx->band_tmp_elems = 0;
     for (int i = 0; i < FEAST_MAX_SLOTS; ++i) { dev_free(ctx->ops[i].uvals_r); dev_free(ctx->ops[i].uvals_c); }
     ctx->problem_ready = false;
 }
@@ -214,6 +219,10 @@ int build_union(feast_ctx* ctx) {
         }
         rowptr[i + 1] = (int64_t)col.size();
     }
+    int bw = 0;
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) bw = std::max(bw, std::abs((int)i - col[e]));
+    ctx->bandwidth = bw;
     const int64_t unnz = (int64_t)col.size();
     if (unnz > INT32_MAX) return feast_fail(ctx, FEAST_ERR_STATE, "union pattern exceeds 2^31 nonzeros");
     ctx->unnz = unnz;
@@ -275,7 +284,11 @@ int build_union(feast_ctx* ctx) {
 int effective_solver(const feast_ctx* ctx) {
     if (ctx->solver != FEAST_SOLVER_AUTO) return ctx->solver;
     if (ctx->storage_dense) return FEAST_SOLVER_DENSE_LU;
-    return ctx->n <= ctx->dense_threshold ? FEAST_SOLVER_DENSE_LU : FEAST_SOLVER_KRYLOV;
+    if (ctx->n <= ctx->dense_threshold) return FEAST_SOLVER_DENSE_LU;
+    // non-symmetric banded operators (2-D discretisations): restarted Krylov stagnates on the shifted
+    // systems, the block-tridiagonal direct solver does not
+    if (!ctx->all_symmetric && ctx->bandwidth > 0 && ctx->bandwidth <= 2048) return FEAST_SOLVER_BANDED_LU;
+    return FEAST_SOLVER_KRYLOV;
 }
 int effective_krylov(const feast_ctx* ctx) {
     if (ctx->krylov != FEAST_KRYLOV_AUTO) return ctx->krylov;
@@ -500,6 +513,24 @@ int solve_shifted(feast_ctx* ctx, int solver, int method, int k, const hc128* co
         if (e1) cudaEventRecord(e1, ctx->stream);
         FEAST_TRY(ensure_block(ctx, ctx->W2));
         FEAST_TRY(dense_getrs(ctx, n, f->lu, f->perm, f->dinv, m, rhs, Y, adjoint));      // ldiv! (or F' \\ R)
+    } else if (solver == FEAST_SOLVER_BANDED_LU) {
+        if (adjoint) return feast_fail(ctx, FEAST_ERR_STATE, "adjoint solves are not available with the banded solver");
+        if (ctx->storage_dense) return feast_fail(ctx, FEAST_ERR_STATE, "the banded solver needs sparse operators");
+        FEAST_TRY(assemble_sparse_Z(ctx, coef, ctx->zvals));
+        BandFactor* bf = &ctx->bscratch;
+        bool need_factor = true;
+        if (ctx->store && k >= 0) {
+            if ((int)ctx->bstored.size() != (int)ctx->znodes.size()) ctx->bstored.resize(ctx->znodes.size());
+            bf = &ctx->bstored[k];
+            need_factor = (bf->lu == nullptr);
+        }
+        if (need_factor) {
+            int info = 0;
+            FEAST_TRY(band_factor(ctx, ctx->zvals, *bf, &info));
+            if (info && !st.info) st.info = info;
+        }
+        if (e1) cudaEventRecord(e1, ctx->stream);
+        FEAST_TRY(band_solve(ctx, *bf, ctx->zvals, m, rhs, Y));
     } else {
         FEAST_TRY(assemble_sparse_Z(ctx, coef, ctx->zvals));
         if (e1) cudaEventRecord(e1, ctx->stream);
@@ -707,7 +738,7 @@ int feast_set_contour(feast_ctx* ctx, int nnodes, const feast_c128* z, const fea
 
 int feast_set_solver(feast_ctx* ctx, int kind, int krylov, double inner_tol, int max_inner, int store) {
     ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
-    ARG_CHECK(ctx, kind >= 0 && kind <= 2, 2, "unknown solver kind");
+    ARG_CHECK(ctx, kind >= 0 && kind <= 3, 2, "unknown solver kind");
     ARG_CHECK(ctx, krylov >= 0 && krylov <= 3, 3, "unknown Krylov method");
     ARG_CHECK(ctx, inner_tol > 0 && inner_tol < 1, 4, "inner_tol must be in (0,1)");
     ARG_CHECK(ctx, max_inner >= 1, 5, "max_inner must be positive");
@@ -939,7 +970,7 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
     std::vector<hc128> d(m);
     hc128 coef[FEAST_MAX_SLOTS];
     const c128* rhs = first_pass ? ctx->X.p : ctx->R.p;
-    const bool can_move_nodes = ctx->nranks > 1 && ctx->auto_balance && !(solver == FEAST_SOLVER_DENSE_LU && ctx->store);
+    const bool can_move_nodes = ctx->nranks > 1 && ctx->auto_balance && !(solver != FEAST_SOLVER_KRYLOV && ctx->store);  // stored factors pin nodes to ranks
     if (can_move_nodes && ctx->have_costs) rebalance_nodes(ctx);
     std::vector<double> cost_local(nnodes, 0.0);
     for (int k = 0; k < nnodes; ++k) {
@@ -1277,7 +1308,16 @@ int feast_factorize(feast_ctx* ctx, const feast_c128* coef, int ncoef, feast_fac
     } else {
         int rc = dev_alloc(ctx, &F->zvals, ctx->unnz);
         if (!rc) rc = assemble_sparse_Z(ctx, cf, F->zvals);
-        if (rc) { delete F; return rc; }
+        if (!rc && F->kind == FEAST_SOLVER_BANDED_LU) {
+            if (!ctx->red_d) {
+                rc = dev_alloc(ctx, &ctx->red_d, ((size_t)1 << 20) / sizeof(double));
+                ctx->red_bytes = (size_t)1 << 20;
+            }
+            int info = 0;
+            if (!rc) rc = band_factor(ctx, F->zvals, F->band, &info);
+            if (!rc && info) rc = feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d", info);
+        }
+        if (rc) { band_free(F->band); dev_free(F->zvals); delete F; return rc; }
         F->symmetric = ctx->all_symmetric;
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1311,6 +1351,9 @@ int feast_solve(feast_ctx* ctx, const feast_factor* F, int64_t n, int nrhs, cons
     int rc_final = 0;
     if (F->kind == FEAST_SOLVER_DENSE_LU) {
         FEAST_TRY(dense_getrs(ctx, n, F->lu.lu, F->lu.perm, F->lu.dinv, m, rhs, ctx->W1.p, conj_transpose != 0));
+    } else if (F->kind == FEAST_SOLVER_BANDED_LU) {
+        if (conj_transpose) return feast_fail(ctx, FEAST_ERR_STATE, "adjoint solves are not available with the banded solver");
+        FEAST_TRY(band_solve(ctx, F->band, F->zvals, m, rhs, ctx->W1.p));
     } else {
         if (conj_transpose && !F->symmetric)
             return feast_fail(ctx, FEAST_ERR_STATE, "adjoint Krylov solve needs a symmetric operator in this build");
@@ -1336,6 +1379,7 @@ int feast_factor_free(feast_ctx* ctx, feast_factor* F) {  // finalize!(F), src/u
     if (ctx) cudaSetDevice(ctx->device);
     dev_free(F->lu.lu); dev_free(F->lu.ipiv); dev_free(F->lu.perm); dev_free(F->lu.dinv);
     dev_free(F->zvals);
+    band_free(F->band);
     delete F;
     return 0;
 }

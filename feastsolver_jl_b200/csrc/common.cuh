@@ -83,10 +83,18 @@ struct DenseLU {             // one stored factorisation (column-major, LAPACK g
     int64_t n = 0;
 };
 
+struct BandFactor {          // block-tridiagonal LU of a banded operator (band.cu): Schur complements S_I factored densely
+    int b = 0, nbk = 0;      // block size (>= half bandwidth) and number of block rows
+    c128* lu = nullptr;      // [nbk][b*b] row-major LU of S_I
+    int* piv = nullptr;      // [nbk][2*b] ipiv then perm
+    c128* dinv = nullptr;    // [nbk][2*b*kDiagNB] diagonal-block inverses of each S_I
+};
+
 struct feast_factor {        // fine-grained plugin handle
     int kind = 0;            // FEAST_SOLVER_DENSE_LU / FEAST_SOLVER_KRYLOV
     DenseLU lu;
-    c128* zvals = nullptr;   // Krylov: assembled union-pattern values
+    c128* zvals = nullptr;   // Krylov / banded: assembled union-pattern values
+    BandFactor band;
     bool symmetric = false;
 };
 
@@ -127,6 +135,11 @@ struct feast_ctx {
     int max_inner = 5000;
     int store = 0;
     std::vector<DenseLU> stored;  // per node (only local nodes populated)
+    std::vector<BandFactor> bstored; // per node, banded solver
+    BandFactor bscratch;          // store=0
+    c128* band_tmp = nullptr;     // 5 x b*b + 4 x b*max(b,m0) work blocks of the banded solver
+    size_t band_tmp_elems = 0;
+    int bandwidth = 0;            // max |i - j| of the union pattern
     bool panel_attr_set = false;
     bool dmma_attr_set = false;
     int dense_threshold = 6000;   // sparse problems up to this n are solved by dense LU

@@ -393,7 +393,8 @@ int dense_build_diag_inverses(feast_ctx* ctx, int64_t n, const c128* LU, c128* d
 }
 
 int dense_getrs(feast_ctx* ctx, int64_t n, const c128* LU, const int* perm_d, const c128* dinv, int m, const c128* Rhs,
-                c128* Y, bool conj_transpose) {
+                c128* Y, bool conj_transpose, c128* work) {
+    if (!work) work = ctx->W2.p;   // n x m scratch
     const int64_t total = n * m;
     int64_t g = (total + 255) / 256, cap = (int64_t)kNumSMs * 16;
     const int grid = (int)(g < cap ? (g < 1 ? 1 : g) : cap);
@@ -401,11 +402,11 @@ int dense_getrs(feast_ctx* ctx, int64_t n, const c128* LU, const int* perm_d, co
         // Y = P * Rhs ; L w = Y ; U y = w      (A = P^T L U  ->  A^-1 = U^-1 L^-1 P)
         permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(n, m, Rhs, Y, perm_d, 0);
         KLAUNCH_CHECK(ctx);
-        if (dinv && ctx->W2.p) {
+        if (dinv && work) {
             // blocked solves: W_k = inv(L_kk) Y_k ; Y_below -= L[below,k] W_k ; then Y_k = inv(U_kk) W_k ;
             // W_above -= U[above,k] Y_k.  Two DMMA GEMMs per diagonal block, ping-ponging Y <-> W.
             const int nb = kDiagNB;
-            c128* W = ctx->W2.p;
+            c128* W = work;
             const c128* dL = dinv;
             const c128* dU = dinv + (size_t)n * nb;
             for (int64_t k0 = 0; k0 < n; k0 += nb) {
@@ -433,7 +434,7 @@ int dense_getrs(feast_ctx* ctx, int64_t n, const c128* LU, const int* perm_d, co
         FEAST_TRY((trsm_rec<false, false>(ctx, (int)n, m, LU, n, 1, false, Y, m, 1)));
     } else {
         // A^H = U^H L^H P : U^H w = b (lower, non-unit, conj) ; L^H v = w (upper, unit, conj) ; y = P^T v
-        c128* tmp = ctx->W2.p;
+        c128* tmp = work;
         CUDA_TRY(ctx, cudaMemcpyAsync(tmp, Rhs, sizeof(c128) * total, cudaMemcpyDeviceToDevice, ctx->stream));
         // T := U^H : T(i,k) = conj(U(k,i)) -> strides swapped
         FEAST_TRY((trsm_rec<true, false>(ctx, (int)n, m, LU, 1, n, true, tmp, m, 1)));

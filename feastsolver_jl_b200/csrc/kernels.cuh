@@ -71,7 +71,12 @@ int dense_getrf(feast_ctx* ctx, int64_t n, c128* Z, int* ipiv_d, int* info_out);
 // perm_d from dense_build_perm (perm[i] = source row of permuted row i).
 // dinv: diagonal-block inverses from dense_build_diag_inverses (may be nullptr -> recursive TRSM)
 int dense_getrs(feast_ctx* ctx, int64_t n, const c128* LU, const int* perm_d, const c128* dinv, int m, const c128* Rhs,
-                c128* Y, bool conj_transpose);
+                c128* Y, bool conj_transpose, c128* work = nullptr);   // work: n x m scratch (default ctx->W2)
+// ---- band.cu: block-tridiagonal direct solver for banded sparse operators
+struct BandFactor;
+int band_factor(feast_ctx* ctx, const c128* zvals, BandFactor& F, int* info);
+int band_solve(feast_ctx* ctx, const BandFactor& F, const c128* zvals, int m, const c128* Rhs, c128* Y);
+void band_free(BandFactor& F);
 int dense_build_diag_inverses(feast_ctx* ctx, int64_t n, const c128* LU, c128* dinv);
 int dense_build_perm(feast_ctx* ctx, int64_t n, const int* ipiv_d, int* perm_d);
 size_t spmm_partials_bytes(int m);

@@ -58,7 +58,8 @@ typedef struct { double re, im; } feast_c128;
                                        /* result produced, stats carry resid.) */
 
 /* ---- enums ---------------------------------------------------------- */
-enum { FEAST_SOLVER_AUTO = 0, FEAST_SOLVER_DENSE_LU = 1, FEAST_SOLVER_KRYLOV = 2 };
+enum { FEAST_SOLVER_AUTO = 0, FEAST_SOLVER_DENSE_LU = 1, FEAST_SOLVER_KRYLOV = 2,
+       FEAST_SOLVER_BANDED_LU = 3 /* block-tridiagonal direct solver for banded sparse operators */ };
 enum { FEAST_KRYLOV_AUTO = 0, FEAST_KRYLOV_COCG = 1, FEAST_KRYLOV_BICGSTAB = 2, FEAST_KRYLOV_GMRES = 3 };
 enum { FEAST_PROBLEM_STANDARD = 0,    /* A x = l x          feast!      src/feast.jl:10-80   */
        FEAST_PROBLEM_GENERALIZED = 1, /* A x = l B x        gen_feast!  src/feast.jl:89-156  */

@@ -124,6 +124,48 @@ def test_dense_lu_solve_plugin_path(fs):
         assert np.abs(Z @ Y - Bm).max() <= 1e-12 * np.abs(Bm).max() * n
 
 
+def test_banded_block_tridiagonal_solver(fs):
+    """Block-tridiagonal direct solver (band.cu) on a non-symmetric banded complex matrix whose size is
+    not a multiple of the block size, through the factorizer / left_divider seam."""
+    from feastsolver_jl_b200 import _lib
+    rng = np.random.default_rng(1)
+    n, bw = 1000, 37
+    diags, offs = [], []
+    for o in range(-bw, bw + 1):
+        if o in (-bw, -3, -1, 0, 1, 2, bw):
+            diags.append(rng.standard_normal(n - abs(o)) + 1j * rng.standard_normal(n - abs(o)) + (6.0 if o == 0 else 0.0))
+            offs.append(o)
+    A = sp.diags(diags, offs, format="csc")
+    z = 0.4 + 0.9j
+    Bm = x0(n, 24, 2)
+    with fs.FeastContext() as ctx:
+        ctx.set_operator(0, A)
+        ctx.set_problem(0, 1, n)
+        ctx.set_solver(kind=_lib.SOLVER_BANDED_LU)
+        F = ctx.factorize([1.0, -z])
+        Y = ctx.solve(F, Bm)
+        ctx.factor_free(F)
+    Z = (A - z * sp.identity(n)).toarray()
+    ref = np.linalg.solve(Z, Bm)
+    assert np.abs(Y - ref).max() <= 1e-11 * np.abs(ref).max()
+    assert np.abs(Z @ Y - Bm).max() <= 1e-11 * np.abs(Bm).max() * np.abs(Z).sum(axis=1).max()
+
+
+def test_nlfeast_banded_matches_dense(fs):
+    """Same butterfly problem solved with the banded solver and with dense LU."""
+    from feastsolver_jl_b200 import workloads as wl
+    from feastsolver_jl_b200 import _lib
+    mb, r, m0, nodes = 24, 0.12, 24, 24
+    coeffs = wl.butterfly_coeffs(mb)
+    X0 = wl.rand_subspace(mb * mb, m0, seed=1)
+    l1, X1, r1 = fs.nlfeast(coeffs, X0.copy(), nodes, 25, c=1 + 1j, r=r, eps=1e-11, solver_opts={"kind": _lib.SOLVER_DENSE_LU})
+    l2, X2, r2 = fs.nlfeast(coeffs, X0.copy(), nodes, 25, c=1 + 1j, r=r, eps=1e-11, solver_opts={"kind": _lib.SOLVER_BANDED_LU})
+    i1, i2 = np.abs(l1 - (1 + 1j)) <= r, np.abs(l2 - (1 + 1j)) <= r
+    assert i1.sum() == i2.sum() == 17
+    match_eigs(l2[i2], l1[i1])
+    assert r2[i2].max() <= 10 * max(r1[i1].max(), 1e-13)
+
+
 def test_singular_matrix_reports_zero_pivot(fs):
     A = np.zeros((8, 8))
     A[0, 0] = 1.0
