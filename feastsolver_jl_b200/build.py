@@ -18,7 +18,7 @@ LIB = os.path.join(OUT_DIR, "libfeast_cuda.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CU_SOURCES = ["api.cu", "spmm.cu", "blockops.cu", "zgemm_dmma.cu", "krylov.cu", "dense.cu", "band.cu"]
-CPP_SOURCES = ["contour.cpp", "nccl_dl.cpp"]
+CPP_SOURCES = ["contour.cpp", "nccl_dl.cpp", "reorder.cpp"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 

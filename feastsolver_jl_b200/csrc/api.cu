@@ -70,6 +70,14 @@ void free_operator(Operator& op) {
 void free_problem_derived(feast_ctx* ctx) {
     dev_free(ctx->u_rowptr);
     dev_free(ctx->u_col);
+    dev_free(ctx->perm_d);
+    dev_free(ctx->t_ptr);
+    dev_free(ctx->t_hptr);
+    dev_free(ctx->t_hidx);
+    dev_free(ctx->u_lcol);
+    ctx->reordered = false;
+    ctx->tiles_ok = false;
+    ctx->ntiles = 0;
     dev_free(ctx->zvals);
     dev_free(ctx->zdense);
     dev_free(ctx->zpiv);
@@ -187,6 +195,16 @@ int csc_to_host_csr(feast_ctx* ctx, int64_t n, const int64_t* colptr, const int6
     return 0;
 }
 
+int effective_solver(const feast_ctx* ctx);
+
+// The rows are renumbered (reorder.cpp) when the inner solves are Krylov: the tiled SpMM is the hot kernel there.
+// Direct solvers keep the natural ordering (the banded one relies on it).  FEAST_REORDER=0 disables.
+bool want_reorder(const feast_ctx* ctx) {
+    static const bool off = getenv("FEAST_REORDER") && atoi(getenv("FEAST_REORDER")) == 0;
+    if (off || ctx->storage_dense) return false;
+    return effective_solver(ctx) == FEAST_SOLVER_KRYLOV;
+}
+
 // Build the union CSR pattern over all sparse / identity slots and the per-slot value arrays.
 int build_union(feast_ctx* ctx) {
     const int64_t n = ctx->n;
@@ -195,10 +213,13 @@ int build_union(feast_ctx* ctx) {
     // pass 1: merged pattern row by row
     std::vector<const HostCSR*> hs;
     bool any_identity = false;
+    bool all_sym = true;
     for (int s = 0; s < ctx->nslots; ++s) {
-        if (ctx->ops[s].kind == OP_CSR) hs.push_back(&ctx->ops[s].host);
-        if (ctx->ops[s].kind == OP_IDENTITY) any_identity = true;
+        if (ctx->ops[s].kind == OP_CSR) { hs.push_back(&ctx->ops[s].host); all_sym = all_sym && ctx->ops[s].host.symmetric; }
+        else if (ctx->ops[s].kind == OP_IDENTITY) any_identity = true;
+        else return feast_fail(ctx, FEAST_ERR_STATE, "slot %d is not set (sparse problem)", s);
     }
+    ctx->all_symmetric = all_sym;
     size_t reserve = 0;
     for (auto* h : hs) reserve = std::max(reserve, (size_t)h->nnz);
     col.reserve(reserve + (any_identity ? n : 0));
@@ -226,21 +247,72 @@ int build_union(feast_ctx* ctx) {
     const int64_t unnz = (int64_t)col.size();
     if (unnz > INT32_MAX) return feast_fail(ctx, FEAST_ERR_STATE, "union pattern exceeds 2^31 nonzeros");
     ctx->unnz = unnz;
+
+    // tile plan (+ renumbering for Krylov inner solves); src[e_new] = e_old maps the permuted union pattern
+    // back to the natural one
+    ctx->reordered = false;
+    ctx->tiles_ok = false;
+    const TileCaps caps = spmm_tile_caps();
+    TilePlan plan;
+    std::vector<int> src;
+    std::vector<int64_t> rowptr_p;
+    std::vector<int> col_p;
+    std::vector<uint16_t> lcol;
+    const bool reorder = want_reorder(ctx);
+    build_tile_order(n, rowptr.data(), col.data(), reorder, caps, plan);
+    if (reorder) {
+        std::vector<int> inv(n);
+        for (int64_t i = 0; i < n; ++i) inv[plan.order[i]] = (int)i;
+        rowptr_p.assign(n + 1, 0);
+        col_p.resize(unnz);
+        src.resize(unnz);
+        std::vector<std::pair<int, int>> rowbuf;
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t old = plan.order[i];
+            rowbuf.clear();
+            for (int64_t e = rowptr[old]; e < rowptr[old + 1]; ++e) rowbuf.emplace_back(inv[col[e]], (int)e);
+            std::sort(rowbuf.begin(), rowbuf.end());
+            int64_t d = rowptr_p[i];
+            for (auto& pr : rowbuf) { col_p[d] = pr.first; src[d] = pr.second; ++d; }
+            rowptr_p[i + 1] = d;
+        }
+        ctx->reordered = true;
+    }
+    const std::vector<int64_t>& rp_use = ctx->reordered ? rowptr_p : rowptr;
+    const std::vector<int>& col_use = ctx->reordered ? col_p : col;
+    if (plan.ok && build_tile_halo(n, rp_use.data(), col_use.data(), plan, lcol) == 0) ctx->tiles_ok = true;
+    ctx->halo_ratio = plan.halo_ratio;
+    ctx->ntiles = (int)plan.tile_ptr.size() - 1;
+
     std::vector<int> rp32(n + 1);
-    for (int64_t i = 0; i <= n; ++i) rp32[i] = (int)rowptr[i];
+    for (int64_t i = 0; i <= n; ++i) rp32[i] = (int)rp_use[i];
     FEAST_TRY(dev_alloc(ctx, &ctx->u_rowptr, n + 1));
     FEAST_TRY(dev_alloc(ctx, &ctx->u_col, unnz));
     // all uploads are ordered on the library stream: it is a NON-BLOCKING stream, so legacy-stream
     // copies from pageable memory would not be ordered against the kernels launched on it
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->u_rowptr, rp32.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->u_col, col.data(), sizeof(int) * unnz, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->u_col, col_use.data(), sizeof(int) * unnz, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->reordered) {
+        FEAST_TRY(dev_alloc(ctx, &ctx->perm_d, n));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->perm_d, plan.order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (ctx->tiles_ok) {
+        FEAST_TRY(dev_alloc(ctx, &ctx->t_ptr, plan.tile_ptr.size()));
+        FEAST_TRY(dev_alloc(ctx, &ctx->t_hptr, plan.halo_ptr.size()));
+        FEAST_TRY(dev_alloc(ctx, &ctx->t_hidx, plan.halo_idx.size() + 1));
+        FEAST_TRY(dev_alloc(ctx, &ctx->u_lcol, unnz + 8));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->t_ptr, plan.tile_ptr.data(), sizeof(int) * plan.tile_ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->t_hptr, plan.halo_ptr.data(), sizeof(int) * plan.halo_ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
+        if (!plan.halo_idx.empty())
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->t_hidx, plan.halo_idx.data(), sizeof(int) * plan.halo_idx.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->u_lcol, lcol.data(), sizeof(uint16_t) * unnz, cudaMemcpyHostToDevice, ctx->stream));
+    }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     // pass 2: per-slot values on the union pattern
-    bool all_sym = true;
     for (int s = 0; s < ctx->nslots; ++s) {
         Operator& op = ctx->ops[s];
-        std::vector<double> rv;
-        std::vector<hc128> cv;
+        std::vector<double> rv, rv2;
+        std::vector<hc128> cv, cv2;
         const bool cplx = (op.kind == OP_CSR) && op.host.is_complex;
         if (cplx) cv.assign(unnz, hc128(0, 0)); else rv.assign(unnz, 0.0);
         if (op.kind == OP_IDENTITY) {
@@ -249,7 +321,7 @@ int build_union(feast_ctx* ctx) {
                 rv[it - col.begin()] = 1.0;
             }
             op.symmetric = true;
-        } else if (op.kind == OP_CSR) {
+        } else {
             const HostCSR& h = op.host;
             for (int64_t i = 0; i < n; ++i) {
                 int64_t u = rowptr[i];
@@ -259,11 +331,12 @@ int build_union(feast_ctx* ctx) {
                 }
             }
             op.symmetric = h.symmetric;
-        } else {
-            return feast_fail(ctx, FEAST_ERR_STATE, "slot %d is not set (sparse problem)", s);
         }
-        all_sym = all_sym && op.symmetric;
         op.is_complex = cplx;
+        if (ctx->reordered) {
+            if (cplx) { cv2.resize(unnz); for (int64_t e = 0; e < unnz; ++e) cv2[e] = cv[src[e]]; cv.swap(cv2); }
+            else { rv2.resize(unnz); for (int64_t e = 0; e < unnz; ++e) rv2[e] = rv[src[e]]; rv.swap(rv2); }
+        }
         if (cplx) {
             FEAST_TRY(dev_alloc(ctx, &op.uvals_c, unnz));
             CUDA_TRY(ctx, cudaMemcpyAsync(op.uvals_c, cv.data(), sizeof(c128) * unnz, cudaMemcpyHostToDevice, ctx->stream));
@@ -276,7 +349,6 @@ int build_union(feast_ctx* ctx) {
         // host copies are kept so that feast_set_problem can be called again (e.g. switching the
         // problem kind); an identity slot keeps its kind and additionally lives on the union pattern
     }
-    ctx->all_symmetric = all_sym;
     FEAST_TRY(dev_alloc(ctx, &ctx->zvals, unnz));
     return 0;
 }
@@ -434,7 +506,7 @@ int download_block(feast_ctx* ctx, const BlockVec& b, feast_c128* H, int64_t ld)
     const int64_t n = ctx->n;
     const int m = ctx->m0;
     if (!b.p) return feast_fail(ctx, FEAST_ERR_STATE, "requested block has not been computed yet");
-    FEAST_TRY(launch_rowmajor_to_colmajor(ctx, n, m, b.p, ctx->stage, n));
+    FEAST_TRY(launch_rowmajor_to_colmajor(ctx, n, m, b.p, ctx->stage, n, ctx->perm_d));
     CUDA_TRY(ctx, cudaMemcpy2DAsync(H, sizeof(c128) * ld, ctx->stage, sizeof(c128) * n, sizeof(c128) * n, m,
                                     cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -743,6 +815,24 @@ int feast_set_solver(feast_ctx* ctx, int kind, int krylov, double inner_tol, int
     ARG_CHECK(ctx, inner_tol > 0 && inner_tol < 1, 4, "inner_tol must be in (0,1)");
     ARG_CHECK(ctx, max_inner >= 1, 5, "max_inner must be positive");
     ctx->solver = kind; ctx->krylov = krylov; ctx->inner_tol = inner_tol; ctx->max_inner = max_inner; ctx->store = store;
+    // the internal row ordering follows the solver kind (Krylov: tiled; direct: natural).  A change after
+    // feast_set_problem rebuilds the device operators from the host copies and drops the subspace blocks.
+    if (ctx->problem_ready && !ctx->storage_dense && want_reorder(ctx) != ctx->reordered) {
+        FEAST_TRY(bind_device(ctx));
+        const int nslots = ctx->nslots;
+        free_problem_derived(ctx);
+        if (ctx->m0 != 0) free_blocks(ctx);
+        ctx->nslots = nslots;
+        FEAST_TRY(build_union(ctx));
+        ctx->problem_ready = true;
+    }
+    return 0;
+}
+
+int feast_layout_info(const feast_ctx* ctx, int* info4, double* halo) {
+    if (!ctx) return feast_fail(nullptr, -1, "argument 1 invalid: null context");
+    if (info4) { info4[0] = ctx->reordered ? 1 : 0; info4[1] = ctx->ntiles; info4[2] = ctx->bandwidth; info4[3] = ctx->tiles_ok ? 1 : 0; }
+    if (halo) *halo = ctx->halo_ratio;
     return 0;
 }
 
@@ -813,7 +903,7 @@ int feast_set_subspace(feast_ctx* ctx, int64_t n, int m0, const feast_c128* X, i
     FEAST_TRY(ensure_block(ctx, ctx->R));
     CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->stage, sizeof(c128) * n, X, sizeof(c128) * ldx, sizeof(c128) * n, m0,
                                     cudaMemcpyHostToDevice, ctx->stream));
-    FEAST_TRY(launch_colmajor_to_rowmajor(ctx, n, m0, ctx->stage, n, ctx->Q.p));
+    FEAST_TRY(launch_colmajor_to_rowmajor(ctx, n, m0, ctx->stage, n, ctx->Q.p, ctx->perm_d));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->X.p, ctx->Q.p, sizeof(c128) * n * m0, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1093,7 +1183,7 @@ int feast_dual_set_subspace(feast_ctx* ctx, int64_t n, int m0, const feast_c128*
     FEAST_TRY(ensure_block(ctx, ctx->Rl));
     CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->stage, sizeof(c128) * n, Xl, sizeof(c128) * ldl, sizeof(c128) * n, m0,
                                     cudaMemcpyHostToDevice, ctx->stream));
-    FEAST_TRY(launch_colmajor_to_rowmajor(ctx, n, m0, ctx->stage, n, ctx->Ql.p));
+    FEAST_TRY(launch_colmajor_to_rowmajor(ctx, n, m0, ctx->stage, n, ctx->Ql.p, ctx->perm_d));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->Xl.p, ctx->Ql.p, sizeof(c128) * n * m0, cudaMemcpyDeviceToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1347,7 +1437,7 @@ int feast_solve(feast_ctx* ctx, const feast_factor* F, int64_t n, int nrhs, cons
                                     cudaMemcpyHostToDevice, ctx->stream));
     FEAST_TRY(ensure_block(ctx, ctx->R));
     c128* rhs = ctx->R.p;
-    FEAST_TRY(launch_colmajor_to_rowmajor(ctx, n, m, ctx->stage, n, rhs));
+    FEAST_TRY(launch_colmajor_to_rowmajor(ctx, n, m, ctx->stage, n, rhs, ctx->perm_d));
     int rc_final = 0;
     if (F->kind == FEAST_SOLVER_DENSE_LU) {
         FEAST_TRY(dense_getrs(ctx, n, F->lu.lu, F->lu.perm, F->lu.dinv, m, rhs, ctx->W1.p, conj_transpose != 0));
@@ -1367,7 +1457,7 @@ int feast_solve(feast_ctx* ctx, const feast_factor* F, int64_t n, int nrhs, cons
         FEAST_TRY(krylov_solve(ctx, method, F->zvals, rhs, ctx->W1.p, ctx->inner_tol, ctx->max_inner, &kr));
         if (!kr.converged) rc_final = FEAST_WARN_INNER_MAXIT;
     }
-    FEAST_TRY(launch_rowmajor_to_colmajor(ctx, n, m, ctx->W1.p, ctx->stage, n));
+    FEAST_TRY(launch_rowmajor_to_colmajor(ctx, n, m, ctx->W1.p, ctx->stage, n, ctx->perm_d));
     CUDA_TRY(ctx, cudaMemcpy2DAsync(Y, sizeof(c128) * ldy, ctx->stage, sizeof(c128) * n, sizeof(c128) * n, m,
                                     cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));

@@ -94,7 +94,8 @@ __global__ void real_to_complex_kernel(int64_t count, const double* __restrict__
 
 // 32x32 tiled transpose between column-major (ld) and row-major (m contiguous)
 template <bool TO_ROWMAJOR>
-__global__ void transpose_kernel(int64_t n, int m, const c128* __restrict__ src, c128* __restrict__ dst, int64_t ld) {
+__global__ void transpose_kernel(int64_t n, int m, const c128* __restrict__ src, c128* __restrict__ dst, int64_t ld,
+                                 const int* __restrict__ perm) {
     __shared__ c128 tile[32][33];
     const int64_t i0 = (int64_t)blockIdx.x * 32;
     const int j0 = blockIdx.y * 32;
@@ -102,7 +103,7 @@ __global__ void transpose_kernel(int64_t n, int m, const c128* __restrict__ src,
         // read column-major: consecutive threads along i
         for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
             const int64_t i = i0 + threadIdx.x; const int j = j0 + jj;
-            if (i < n && j < m) tile[jj][threadIdx.x] = src[(int64_t)j * ld + i];
+            if (i < n && j < m) tile[jj][threadIdx.x] = src[(int64_t)j * ld + (perm ? perm[i] : i)];
         }
         __syncthreads();
         for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) {
@@ -117,7 +118,7 @@ __global__ void transpose_kernel(int64_t n, int m, const c128* __restrict__ src,
         __syncthreads();
         for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
             const int64_t i = i0 + threadIdx.x; const int j = j0 + jj;
-            if (i < n && j < m) dst[(int64_t)j * ld + i] = tile[jj][threadIdx.x];
+            if (i < n && j < m) dst[(int64_t)j * ld + (perm ? perm[i] : i)] = tile[jj][threadIdx.x];
         }
     }
 }
@@ -238,15 +239,15 @@ int launch_accumulate(feast_ctx* ctx, int64_t n, int m, const c128* X, const c12
     KLAUNCH_CHECK(ctx);
     return 0;
 }
-int launch_colmajor_to_rowmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, int64_t ld, c128* dst) {
+int launch_colmajor_to_rowmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, int64_t ld, c128* dst, const int* perm) {
     dim3 grid(ceil_div(n, 32), ceil_div(m, 32)), block(32, 8);
-    transpose_kernel<true><<<grid, block, 0, ctx->stream>>>(n, m, src, dst, ld);
+    transpose_kernel<true><<<grid, block, 0, ctx->stream>>>(n, m, src, dst, ld, perm);
     KLAUNCH_CHECK(ctx);
     return 0;
 }
-int launch_rowmajor_to_colmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, c128* dst, int64_t ld) {
+int launch_rowmajor_to_colmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, c128* dst, int64_t ld, const int* perm) {
     dim3 grid(ceil_div(n, 32), ceil_div(m, 32)), block(32, 8);
-    transpose_kernel<false><<<grid, block, 0, ctx->stream>>>(n, m, src, dst, ld);
+    transpose_kernel<false><<<grid, block, 0, ctx->stream>>>(n, m, src, dst, ld, perm);
     KLAUNCH_CHECK(ctx);
     return 0;
 }

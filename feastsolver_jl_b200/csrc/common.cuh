@@ -118,6 +118,17 @@ struct feast_ctx {
     int* u_rowptr = nullptr;
     int* u_col = nullptr;
     bool all_symmetric = false;
+    // internal layout of the sparse path (reorder.cpp / spmm.cu): rows cut into tiles whose referenced block rows
+    // fit in shared memory; with Krylov inner solves the rows are renumbered so that the tiles are compact
+    int* perm_d = nullptr;        // new -> old row map (nullptr: natural order); applied on upload / download
+    bool reordered = false;
+    bool tiles_ok = false;        // tile plan usable by the tiled SpMM
+    int ntiles = 0;
+    int* t_ptr = nullptr;         // [ntiles + 1] first row of each tile
+    int* t_hptr = nullptr;        // [ntiles + 1] halo list offsets
+    int* t_hidx = nullptr;        // halo rows per tile
+    uint16_t* u_lcol = nullptr;   // [unnz] tile-local column numbers (own rows, then the halo list)
+    double halo_ratio = 0.0;      // halo rows per row (diagnostic)
     c128* zvals = nullptr;        // assembled shifted operator on the union pattern
     c128* zdense = nullptr;       // assembled dense shifted operator (n x n col-major)
     int*  zpiv = nullptr;

@@ -1,6 +1,7 @@
 // Kernel launchers (all enqueue on ctx->stream and return a feast status code).
 #pragma once
 #include "common.cuh"
+#include "reorder.h"
 
 // ---- spmm.cu ---------------------------------------------------------------
 // Y(n x m, row-major ld=ldy) = S * X(n x m, row-major ld=ldx); S = CSR(rowptr,col,val),
@@ -43,8 +44,12 @@ int launch_residual_combine(feast_ctx* ctx, int64_t n, int m, c128* AX_inout_R, 
 int launch_accumulate(feast_ctx* ctx, int64_t n, int m, const c128* X, const c128* Y, const c128* d_d,
                       c128* Q, c128* Q1, hc128 z, bool first_pass);
 // layout conversion between host column-major (ld) and device row-major blocks
-int launch_colmajor_to_rowmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, int64_t ld, c128* dst);
-int launch_rowmajor_to_colmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, c128* dst, int64_t ld);
+// perm (device, new -> old row map, may be nullptr): device row i holds host row perm[i]
+int launch_colmajor_to_rowmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, int64_t ld, c128* dst, const int* perm = nullptr);
+int launch_rowmajor_to_colmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, c128* dst, int64_t ld, const int* perm = nullptr);
+// ---- spmm.cu: capacities of the tiled SpMM (shared-memory rows / staged nonzeros / rows per tile)
+struct TileCaps;
+TileCaps spmm_tile_caps();
 int launch_real_to_complex(feast_ctx* ctx, int64_t count, const double* src, c128* dst);
 int launch_conj(feast_ctx* ctx, int64_t count, const c128* src, c128* dst);  // dst = conj(src), may alias
 // Z(n x n) = sum_i coef[i] * D_i (dense col-major slots; identity slots add coef to the diagonal)

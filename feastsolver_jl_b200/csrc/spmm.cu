@@ -178,17 +178,222 @@ int spmm_dispatch(feast_ctx* ctx, int n, int m, const int* rowptr, const int* co
     return feast_fail(ctx, FEAST_ERR_STATE, "spmm: column block wider than 128 must be chunked by the caller");
 }
 
+
+// ------------------------------------------------------------------ tiled SpMM (the Krylov hot kernel)
+// One CTA pass = one tile of consecutive matrix rows (tile plan: reorder.cpp) x one slab of G <= 32 columns:
+//   * every row of the input block the tile references -- its own rows, then its halo list -- is brought
+//     into shared memory by bulk async copies (cp.async.bulk -> UBLKCP, completion on an mbarrier); the tile's
+//     CSR slice (values + 16-bit tile-local column numbers) is staged the same way, once per tile;
+//   * the products are then computed ENTIRELY out of shared memory (LDS + DFMA): no long-latency load sits in
+//     the inner loop, the memory-level parallelism is the copy engine's, not the register file's;
+//   * L2->SM traffic per SpMM = (1 + halo/rows) reads of X; with the tile ordering ~2.1 instead of ~5.5.
+// 2 CTAs of 512 threads per SM: one computes while the other waits for its copies.
+constexpr int kTiledThreads = 512;
+constexpr int kTiledSmemBudget = 115712;   // (233472 B per SM) / 2 CTAs - 1 KB system reservation each
+constexpr int kRowsCap = 192;              // block rows (tile + halo) resident per CTA: 192 x 32 x 16 B = 96 KB
+constexpr int kNnzCap = 704;               // staged nonzeros per tile
+constexpr int kTileMax = 160;              // rows per tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <typename VT> struct TiledSmem {
+    static constexpr __host__ __device__ size_t xs_bytes(int G) { return (size_t)kRowsCap * G * sizeof(c128); }
+    static constexpr size_t vs_bytes = (size_t)(kNnzCap + 8) * sizeof(VT);
+    static constexpr size_t ls_bytes = (((size_t)(kNnzCap + 8) * sizeof(uint16_t)) + 15) & ~(size_t)15;
+    static constexpr size_t rs_bytes = (size_t)(kTileMax + 4) * sizeof(int);
+    static constexpr __host__ __device__ size_t total(int G) { return xs_bytes(G) + vs_bytes + ls_bytes + rs_bytes; }
+};
+
+// G lanes own one row of the slab at a time (one accumulator per lane; up to 8 products in flight).
+// m <= 2*G: the launch covers one or two slabs.
+template <typename VT, int G, bool DOT>
+__global__ void __launch_bounds__(kTiledThreads, 2)
+spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* __restrict__ t_hptr,
+                  const int* __restrict__ t_hidx, const int* __restrict__ rowptr, const uint16_t* __restrict__ lcol,
+                  const VT* __restrict__ val, const c128* __restrict__ X, int ldx, c128* __restrict__ Y, int ldy,
+                  double* __restrict__ partials) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t mbar;
+    c128* xs = (c128*)smem_raw;                                                 // [kRowsCap][SW]
+    VT* vs = (VT*)(smem_raw + TiledSmem<VT>::xs_bytes(G));                      // [kNnzCap + 8]
+    uint16_t* ls = (uint16_t*)((unsigned char*)vs + TiledSmem<VT>::vs_bytes);   // [kNnzCap + 8]
+    int* rs = (int*)((unsigned char*)ls + TiledSmem<VT>::ls_bytes);             // [kTileMax + 1]
+    constexpr int UPW = 32 / G;   // rows per warp
+    constexpr int NW = kTiledThreads / 32;
+    constexpr int U = 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane % G, sub = lane / G;
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t phase = 0;
+    c128 dacc[2];
+    dacc[0] = cmake(0.0, 0.0);
+    dacc[1] = cmake(0.0, 0.0);
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = __ldg(t_ptr + tile), rows = __ldg(t_ptr + tile + 1) - r0;
+        const int hp = __ldg(t_hptr + tile), nref = rows + __ldg(t_hptr + tile + 1) - hp;   // own rows + halo rows
+        const int e_lo = __ldg(rowptr + r0), e_hi = __ldg(rowptr + r0 + rows);
+        const int ea = e_lo & ~7;                      // 16-byte aligned start of the CSR slice (u16 columns)
+        int eb = e_hi & ~7;                            // bulk part ends here; [eb, e_hi) is copied by threads
+        if (eb < ea) eb = ea;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int j0 = s * G;
+            if (j0 >= m) break;
+            const int SW = (m - j0) < G ? (m - j0) : G;
+            const uint32_t rowbytes = (uint32_t)SW * (uint32_t)sizeof(c128);
+            if (tid == 0) {
+                uint32_t bytes = (uint32_t)nref * rowbytes;
+                if (s == 0) bytes += (uint32_t)(eb - ea) * (uint32_t)(sizeof(VT) + sizeof(uint16_t));
+                mbar_expect_tx(&mbar, bytes);
+            }
+            __syncthreads();   // the previous pass has finished reading shared memory; the barrier is armed
+            for (int t = tid; t < nref; t += kTiledThreads) {
+                const int srow = t < rows ? r0 + t : __ldg(t_hidx + hp + (t - rows));
+                bulk_g2s(xs + (size_t)t * SW, X + (int64_t)srow * ldx + j0, rowbytes, &mbar);
+            }
+            if (s == 0) {
+                if (eb > ea) {
+                    if (tid == 32) bulk_g2s(vs, val + ea, (uint32_t)(eb - ea) * (uint32_t)sizeof(VT), &mbar);
+                    if (tid == 64) bulk_g2s(ls, lcol + ea, (uint32_t)(eb - ea) * (uint32_t)sizeof(uint16_t), &mbar);
+                }
+                for (int t = tid; t <= rows; t += kTiledThreads) rs[t] = __ldg(rowptr + r0 + t) - ea;
+                for (int e = eb + tid; e < e_hi; e += kTiledThreads) { ls[e - ea] = lcol[e]; vs[e - ea] = __ldg(val + e); }
+            }
+            __syncthreads();   // row pointers / slice tail visible
+            mbar_wait(&mbar, phase);
+            phase ^= 1u;
+
+            const int gg = g < SW ? g : 0;
+            for (int lr = warp * UPW + sub; lr < rows; lr += NW * UPW) {
+                const int e0 = rs[lr], e1 = rs[lr + 1];
+                c128 acc = cmake(0.0, 0.0);
+                for (int e = e0; e < e1; e += U) {
+                    c128 xv[U];
+#pragma unroll
+                    for (int k = 0; k < U; ++k) {
+                        const int lc = (e + k < e1) ? (int)ls[e + k] : lr;   // padding entries read the own row
+                        xv[k] = xs[(size_t)lc * SW + gg];
+                    }
+#pragma unroll
+                    for (int k = 0; k < U; ++k)
+                        if (e + k < e1) ValOps<VT>::fma(acc, vs[e + k], xv[k]);
+                }
+                if (g < SW) {
+                    Y[(int64_t)(r0 + lr) * ldy + j0 + g] = acc;
+                    if (DOT) cfma(dacc[s], xs[(size_t)lr * SW + g], acc);
+                }
+            }
+        }
+    }
+    if (DOT) {
+        __syncthreads();
+        // the tile buffer is free now: reuse it for the cross-warp reduction.  slot = (warp, sub), 2 slabs each
+        double* sred = (double*)smem_raw;   // [NW * UPW][2 slabs][2 * G]
+        const int slot = warp * UPW + sub;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            sred[((size_t)slot * 2 + s) * 2 * G + 2 * g] = dacc[s].x;
+            sred[((size_t)slot * 2 + s) * 2 * G + 2 * g + 1] = dacc[s].y;
+        }
+        __syncthreads();
+        for (int t = tid; t < 2 * m; t += kTiledThreads) {
+            const int j = t >> 1, s = j / G, gq = j - s * G;
+            double acc = 0.0;
+            for (int sl = 0; sl < NW * UPW; ++sl) acc += sred[((size_t)sl * 2 + s) * 2 * G + 2 * gq + (t & 1)];
+            partials[(int64_t)blockIdx.x * 2 * m + t] = acc;
+        }
+    }
+}
+
+template <typename VT, int G>
+int spmm_tiled_launch(feast_ctx* ctx, int m, const VT* val, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
+    const size_t smem = TiledSmem<VT>::total(G) < 16384 ? 16384 : TiledSmem<VT>::total(G);
+    static_assert(TiledSmem<VT>::total(32) <= (size_t)kTiledSmemBudget, "tile does not fit 2 CTAs per SM");
+    const int ntiles = ctx->ntiles;
+    const int grid = ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs;
+    static bool attr_done_dot[64] = {}, attr_done[64] = {};   // per device (function attributes are per context)
+    const int dev = ctx->device & 63;
+    if (dot_out) {
+        auto kern = spmm_tiled_kernel<VT, G, true>;
+        if (!attr_done_dot[dev]) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmemBudget));
+            attr_done_dot[dev] = true;
+        }
+        kern<<<grid, kTiledThreads, smem, ctx->stream>>>(m, ntiles, ctx->t_ptr, ctx->t_hptr, ctx->t_hidx, ctx->u_rowptr, ctx->u_lcol,
+                                                          val, X, ldx, Y, ldy, ctx->red_d);
+        KLAUNCH_CHECK(ctx);
+        reduce_partials_kernel<<<ceil_div(2 * m * 32, 128), 128, 0, ctx->stream>>>(ctx->red_d, grid, 2 * m, (double*)dot_out);
+        KLAUNCH_CHECK(ctx);
+    } else {
+        auto kern = spmm_tiled_kernel<VT, G, false>;
+        if (!attr_done[dev]) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmemBudget));
+            attr_done[dev] = true;
+        }
+        kern<<<grid, kTiledThreads, smem, ctx->stream>>>(m, ntiles, ctx->t_ptr, ctx->t_hptr, ctx->t_hidx, ctx->u_rowptr, ctx->u_lcol,
+                                                          val, X, ldx, Y, ldy, nullptr);
+        KLAUNCH_CHECK(ctx);
+    }
+    return 0;
+}
+
+template <typename VT>
+int spmm_tiled_dispatch(feast_ctx* ctx, int m, const VT* val, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
+    if (m <= 4) return spmm_tiled_launch<VT, 4>(ctx, m, val, X, ldx, Y, ldy, dot_out);
+    if (m <= 8) return spmm_tiled_launch<VT, 8>(ctx, m, val, X, ldx, Y, ldy, dot_out);
+    if (m <= 16) return spmm_tiled_launch<VT, 16>(ctx, m, val, X, ldx, Y, ldy, dot_out);
+    return spmm_tiled_launch<VT, 32>(ctx, m, val, X, ldx, Y, ldy, dot_out);   // m <= 64: one or two slabs of 32 columns
+}
+
 }  // namespace
 
 size_t spmm_partials_bytes(int m) { return (size_t)kNumSMs * 8 * 2 * (size_t)(m < 128 ? 128 : m) * sizeof(double); }
 
+TileCaps spmm_tile_caps() { return TileCaps{kRowsCap, kNnzCap, kTileMax}; }
+
 int launch_spmm(feast_ctx* ctx, int64_t n, int m, const int* rowptr, const int* col, const double* rvals,
                 const c128* cvals, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
-    // column blocks wider than 128 are processed in chunks of 128 (registers hold CPL<=4 accumulators)
-    for (int j0 = 0; j0 < m; j0 += 128) {
-        const int mc = (m - j0) < 128 ? (m - j0) : 128;
+    // tiled kernel on the union pattern (column chunks of 64 = two slabs of 32);
+    // FEAST_SPMM_TILED=0 selects the row-per-warp kernel (kept for A/B measurements)
+    static const bool tiled_off = getenv("FEAST_SPMM_TILED") && atoi(getenv("FEAST_SPMM_TILED")) == 0;
+    const bool tiled = !tiled_off && ctx->tiles_ok && rowptr == ctx->u_rowptr && col == ctx->u_col;
+    const int chunk = tiled ? 64 : 128;
+    for (int j0 = 0; j0 < m; j0 += chunk) {
+        const int mc = (m - j0) < chunk ? (m - j0) : chunk;
         c128* dchunk = dot_out ? dot_out + j0 : nullptr;
-        int rc = rvals ? spmm_dispatch<double>(ctx, (int)n, mc, rowptr, col, rvals, X + j0, ldx, Y + j0, ldy, dchunk)
+        int rc;
+        if (tiled)
+            rc = rvals ? spmm_tiled_dispatch<double>(ctx, mc, rvals, X + j0, ldx, Y + j0, ldy, dchunk)
+                       : spmm_tiled_dispatch<c128>(ctx, mc, cvals, X + j0, ldx, Y + j0, ldy, dchunk);
+        else
+            rc = rvals ? spmm_dispatch<double>(ctx, (int)n, mc, rowptr, col, rvals, X + j0, ldx, Y + j0, ldy, dchunk)
                        : spmm_dispatch<c128>(ctx, (int)n, mc, rowptr, col, cvals, X + j0, ldx, Y + j0, ldy, dchunk);
         if (rc) return rc;
     }

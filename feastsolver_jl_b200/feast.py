@@ -109,6 +109,14 @@ class FeastContext:
     def set_solver(self, kind=_lib.SOLVER_AUTO, krylov=_lib.KRYLOV_AUTO, inner_tol=1e-8, max_inner=4000, store=False):
         self._ck(self.lib.feast_set_solver(self.h, kind, krylov, float(inner_tol), int(max_inner), int(bool(store))))
 
+    def layout_info(self):
+        """Internal layout of the sparse path: renumbered?, tiles, natural bandwidth, tiled SpMM in use, halo rows per row."""
+        info = np.zeros(4, dtype=np.int32)
+        halo = C.c_double(0.0)
+        self._ck(self.lib.feast_layout_info(self.h, _lib.ptr(info), C.byref(halo)))
+        return {"reordered": bool(info[0]), "ntiles": int(info[1]), "bandwidth": int(info[2]), "tiled_spmm": bool(info[3]),
+                "halo_rows_per_row": halo.value}
+
     def set_node_owners(self, owners):
         o = np.ascontiguousarray(owners, dtype=np.int32)
         self._ck(self.lib.feast_set_node_owners(self.h, len(o), _lib.ptr(o)))

@@ -195,6 +195,17 @@ FEAST_API int  feast_timer_stop(feast_ctx* ctx, float* ms);
 FEAST_API int64_t feast_launch_count(const feast_ctx* ctx);
 /* device-timed phases since the last reset (ms): [0]=project [1]=recover [2]=contour_apply */
 FEAST_API int  feast_phase_times(feast_ctx* ctx, double* ms3, int reset);
+/* Internal layout of the sparse path (no reference counterpart: UMFPACK reorders internally as
+ * well).  The rows are cut into tiles whose referenced rows of the n x m0 block fit in shared
+ * memory (tiled SpMM); with Krylov inner solves the rows are renumbered so that the tiles are
+ * compact.  info[0] = 1 if renumbered, info[1] = number of tiles, info[2] = max |i - j| of the
+ * union pattern in the NATURAL ordering, info[3] = 1 if the tiled SpMM is in use; halo = rows
+ * fetched from outside a tile per row.  Blocks cross the ABI in the caller's ordering.          */
+FEAST_API int  feast_layout_info(const feast_ctx* ctx, int* info4, double* halo);
+/* Host-only (no device): the tile plan the library would build for a 0-based CSR pattern with the
+ * given capacities; order[i_new] = i_old (may be NULL).  Returns 1 if a single row exceeds them. */
+FEAST_API int  feast_debug_tile_plan(int64_t n, const int64_t* rowptr, const int* col, int reorder, int rows_cap,
+                                     int nnz_cap, int tile_max, int* order, int* ntiles, double* halo_ratio);
 
 #ifdef __cplusplus
 }

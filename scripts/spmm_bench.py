@@ -18,6 +18,7 @@ X0 = wl.rand_subspace(n, a.m0, seed=0)
 ctx = fs.FeastContext()
 ctx.set_operator(0, A); ctx.set_operator(1, B); ctx.set_problem(1, 2, n)
 ctx.set_subspace(X0)
+print(json.dumps({"layout": ctx.layout_info()}))
 _, ms = ctx.apply_operator(0, which=0, download=False, reps=a.reps)
 bytes_real = A.nnz * 12 + 4 * (n + 1) + 32 * n * a.m0
 print(json.dumps({"kernel": "spmm real", "ms": ms, "GBs": bytes_real / ms / 1e6}))

@@ -118,3 +118,33 @@ def test_workload_generators():
     assert np.abs(ex - an).max() < 1e-11
     c, r, cnt = wl.c2_slice(6, target=10)
     assert np.sum(np.abs(an - c) <= r) == cnt
+
+
+def test_tile_plan_is_a_permutation_and_cuts_the_halo(lib):
+    """Host side of the tiled SpMM (csrc/reorder.cpp): the greedy graph-growing order is a permutation, respects
+    the shared-memory capacities, and references far fewer out-of-tile rows than the natural order of a 3-D grid."""
+    import scipy.sparse as sp
+    from feastsolver_jl_b200 import _lib, workloads as wl
+    A, _ = wl.laplacian3d_pencil(24)
+    A = sp.csr_matrix(A)
+    n = A.shape[0]
+    rowptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    col = np.ascontiguousarray(A.indices, dtype=np.int32)
+    res = {}
+    for reorder in (0, 1):
+        order = np.zeros(n, dtype=np.int32)
+        nt, halo = C.c_int(0), C.c_double(0.0)
+        rc = lib.feast_debug_tile_plan(n, _lib.ptr(rowptr), _lib.ptr(col), reorder, 192, 704, 160, _lib.ptr(order),
+                                       C.byref(nt), C.byref(halo))
+        assert rc == 0
+        assert np.array_equal(np.sort(order), np.arange(n))
+        res[reorder] = (nt.value, halo.value, order)
+    assert np.array_equal(res[0][2], np.arange(n))          # natural order kept when not renumbering
+    assert res[1][1] < 0.45 * res[0][1]                       # halo rows per row: ~1.2 vs ~4
+    assert res[1][1] < 1.6
+    # capacity: a row with more distinct columns than the shared-memory row capacity cannot be tiled
+    D = sp.csr_matrix(np.ones((1, 300)))
+    Dfull = sp.vstack([D, sp.csr_matrix((299, 300))]).tocsr()
+    rc = lib.feast_debug_tile_plan(300, _lib.ptr(np.ascontiguousarray(Dfull.indptr, dtype=np.int64)),
+                                   _lib.ptr(np.ascontiguousarray(Dfull.indices, dtype=np.int32)), 1, 192, 704, 160, None, None, None)
+    assert rc == 1
