@@ -244,54 +244,61 @@ int build_union(feast_ctx* ctx) {
     for (int64_t i = 0; i < n; ++i)
         for (int64_t e = rowptr[i]; e < rowptr[i + 1]; ++e) bw = std::max(bw, std::abs((int)i - col[e]));
     ctx->bandwidth = bw;
-    const int64_t unnz = (int64_t)col.size();
-    if (unnz > INT32_MAX) return feast_fail(ctx, FEAST_ERR_STATE, "union pattern exceeds 2^31 nonzeros");
-    ctx->unnz = unnz;
+    const int64_t nnz_nat = (int64_t)col.size();
 
-    // tile plan (+ renumbering for Krylov inner solves); src[e_new] = e_old maps the permuted union pattern
-    // back to the natural one
+    // Device layout of the union pattern: rows (re)ordered by the tile plan and every row PADDED to a multiple of
+    // 8 entries (column -1, value 0 in every slot), so that each row's 16-bit tile-local column numbers are one
+    // aligned 16-byte word per 8 entries and every tile's CSR slice is 16-byte aligned for the bulk copies
+    // (spmm.cu).  src[e] = entry of the natural union pattern behind device entry e (-1 for padding).
     ctx->reordered = false;
     ctx->tiles_ok = false;
     const TileCaps caps = spmm_tile_caps();
     TilePlan plan;
-    std::vector<int> src;
-    std::vector<int64_t> rowptr_p;
-    std::vector<int> col_p;
-    std::vector<uint16_t> lcol;
     const bool reorder = want_reorder(ctx);
     build_tile_order(n, rowptr.data(), col.data(), reorder, caps, plan);
+    std::vector<int> inv;
     if (reorder) {
-        std::vector<int> inv(n);
+        inv.resize(n);
         for (int64_t i = 0; i < n; ++i) inv[plan.order[i]] = (int)i;
-        rowptr_p.assign(n + 1, 0);
-        col_p.resize(unnz);
-        src.resize(unnz);
-        std::vector<std::pair<int, int>> rowbuf;
-        for (int64_t i = 0; i < n; ++i) {
-            const int64_t old = plan.order[i];
-            rowbuf.clear();
-            for (int64_t e = rowptr[old]; e < rowptr[old + 1]; ++e) rowbuf.emplace_back(inv[col[e]], (int)e);
-            std::sort(rowbuf.begin(), rowbuf.end());
-            int64_t d = rowptr_p[i];
-            for (auto& pr : rowbuf) { col_p[d] = pr.first; src[d] = pr.second; ++d; }
-            rowptr_p[i + 1] = d;
-        }
         ctx->reordered = true;
     }
-    const std::vector<int64_t>& rp_use = ctx->reordered ? rowptr_p : rowptr;
-    const std::vector<int>& col_use = ctx->reordered ? col_p : col;
-    if (plan.ok && build_tile_halo(n, rp_use.data(), col_use.data(), plan, lcol) == 0) ctx->tiles_ok = true;
+    std::vector<int64_t> rowptr_f(n + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t old = reorder ? plan.order[i] : i;
+        rowptr_f[i + 1] = rowptr_f[i] + ((rowptr[old + 1] - rowptr[old] + 7) & ~(int64_t)7);
+    }
+    const int64_t unnz = rowptr_f[n];
+    if (unnz > INT32_MAX) return feast_fail(ctx, FEAST_ERR_STATE, "union pattern exceeds 2^31 nonzeros");
+    ctx->unnz = unnz;
+    std::vector<int> col_f((size_t)unnz, -1), src((size_t)unnz, -1);
+    {
+        std::vector<std::pair<int, int>> rowbuf;
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t old = reorder ? plan.order[i] : i;
+            int64_t d = rowptr_f[i];
+            if (reorder) {
+                rowbuf.clear();
+                for (int64_t e = rowptr[old]; e < rowptr[old + 1]; ++e) rowbuf.emplace_back(inv[col[e]], (int)e);
+                std::sort(rowbuf.begin(), rowbuf.end());
+                for (auto& pr : rowbuf) { col_f[d] = pr.first; src[d] = pr.second; ++d; }
+            } else {
+                for (int64_t e = rowptr[old]; e < rowptr[old + 1]; ++e) { col_f[d] = col[e]; src[d] = (int)e; ++d; }
+            }
+        }
+    }
+    std::vector<uint16_t> lcol;
+    if (plan.ok && build_tile_halo(n, rowptr_f.data(), col_f.data(), plan, lcol) == 0) ctx->tiles_ok = true;
     ctx->halo_ratio = plan.halo_ratio;
     ctx->ntiles = (int)plan.tile_ptr.size() - 1;
 
     std::vector<int> rp32(n + 1);
-    for (int64_t i = 0; i <= n; ++i) rp32[i] = (int)rp_use[i];
+    for (int64_t i = 0; i <= n; ++i) rp32[i] = (int)rowptr_f[i];
     FEAST_TRY(dev_alloc(ctx, &ctx->u_rowptr, n + 1));
     FEAST_TRY(dev_alloc(ctx, &ctx->u_col, unnz));
     // all uploads are ordered on the library stream: it is a NON-BLOCKING stream, so legacy-stream
     // copies from pageable memory would not be ordered against the kernels launched on it
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->u_rowptr, rp32.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->u_col, col_use.data(), sizeof(int) * unnz, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->u_col, col_f.data(), sizeof(int) * unnz, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->reordered) {
         FEAST_TRY(dev_alloc(ctx, &ctx->perm_d, n));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->perm_d, plan.order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -300,7 +307,7 @@ int build_union(feast_ctx* ctx) {
         FEAST_TRY(dev_alloc(ctx, &ctx->t_ptr, plan.tile_ptr.size()));
         FEAST_TRY(dev_alloc(ctx, &ctx->t_hptr, plan.halo_ptr.size()));
         FEAST_TRY(dev_alloc(ctx, &ctx->t_hidx, plan.halo_idx.size() + 1));
-        FEAST_TRY(dev_alloc(ctx, &ctx->u_lcol, unnz + 8));
+        FEAST_TRY(dev_alloc(ctx, &ctx->u_lcol, unnz));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->t_ptr, plan.tile_ptr.data(), sizeof(int) * plan.tile_ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->t_hptr, plan.halo_ptr.data(), sizeof(int) * plan.halo_ptr.size(), cudaMemcpyHostToDevice, ctx->stream));
         if (!plan.halo_idx.empty())
@@ -308,13 +315,13 @@ int build_union(feast_ctx* ctx) {
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->u_lcol, lcol.data(), sizeof(uint16_t) * unnz, cudaMemcpyHostToDevice, ctx->stream));
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    // pass 2: per-slot values on the union pattern
+    // pass 2: per-slot values, first on the natural union pattern, then gathered into the device layout
     for (int s = 0; s < ctx->nslots; ++s) {
         Operator& op = ctx->ops[s];
         std::vector<double> rv, rv2;
         std::vector<hc128> cv, cv2;
         const bool cplx = (op.kind == OP_CSR) && op.host.is_complex;
-        if (cplx) cv.assign(unnz, hc128(0, 0)); else rv.assign(unnz, 0.0);
+        if (cplx) cv.assign(nnz_nat, hc128(0, 0)); else rv.assign(nnz_nat, 0.0);
         if (op.kind == OP_IDENTITY) {
             for (int64_t i = 0; i < n; ++i) {
                 auto it = std::lower_bound(col.begin() + rowptr[i], col.begin() + rowptr[i + 1], (int)i);
@@ -333,17 +340,17 @@ int build_union(feast_ctx* ctx) {
             op.symmetric = h.symmetric;
         }
         op.is_complex = cplx;
-        if (ctx->reordered) {
-            if (cplx) { cv2.resize(unnz); for (int64_t e = 0; e < unnz; ++e) cv2[e] = cv[src[e]]; cv.swap(cv2); }
-            else { rv2.resize(unnz); for (int64_t e = 0; e < unnz; ++e) rv2[e] = rv[src[e]]; rv.swap(rv2); }
-        }
         if (cplx) {
+            cv2.assign(unnz, hc128(0, 0));
+            for (int64_t e = 0; e < unnz; ++e) if (src[e] >= 0) cv2[e] = cv[src[e]];
             FEAST_TRY(dev_alloc(ctx, &op.uvals_c, unnz));
-            CUDA_TRY(ctx, cudaMemcpyAsync(op.uvals_c, cv.data(), sizeof(c128) * unnz, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(op.uvals_c, cv2.data(), sizeof(c128) * unnz, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         } else {
+            rv2.assign(unnz, 0.0);
+            for (int64_t e = 0; e < unnz; ++e) if (src[e] >= 0) rv2[e] = rv[src[e]];
             FEAST_TRY(dev_alloc(ctx, &op.uvals_r, unnz));
-            CUDA_TRY(ctx, cudaMemcpyAsync(op.uvals_r, rv.data(), sizeof(double) * unnz, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(op.uvals_r, rv2.data(), sizeof(double) * unnz, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         }
         // host copies are kept so that feast_set_problem can be called again (e.g. switching the

@@ -24,7 +24,7 @@ __global__ void scatter_block_kernel(int n, int b, int I, int J, const int* __re
     const int c0 = J * b;
     for (int e = rowptr[row] + lane; e < rowptr[row + 1]; e += 32) {
         const int c = col[e] - c0;
-        if (c >= 0 && c < b) dst[(size_t)warp * b + c] = zvals[e];
+        if (col[e] >= 0 && c >= 0 && c < b) dst[(size_t)warp * b + c] = zvals[e];   // col < 0: padding entry
     }
 }
 // dst[r, :] = (r < rows ? src[r, :] : 0) for a b x m block

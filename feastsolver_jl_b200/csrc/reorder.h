@@ -6,8 +6,9 @@
 
 struct TileCaps {
     int rows_cap;   // rows of the input block a CTA can hold in shared memory (tile rows + halo rows)
-    int nnz_cap;    // nonzeros of a tile whose CSR slice is staged in shared memory
+    int64_t nnz_cap; // (padded) nonzeros of a tile whose CSR slice is staged in shared memory
     int tile_max;   // max rows of a tile
+    int domain_rows; // > 0: tiles are grown inside compact domains of about this many rows (L2 locality of the sweep)
 };
 
 struct TilePlan {

@@ -55,11 +55,11 @@ spmm_csr_kernel(int n, int m, const int* __restrict__ rowptr, const int* __restr
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
                     const int j = g + k * G;
-                    const bool ok = j < m;
-                    x0[k] = ok ? __ldg(X + (int64_t)c0 * ldx + j) : cmake(0, 0);
-                    x1[k] = ok ? __ldg(X + (int64_t)c1 * ldx + j) : cmake(0, 0);
-                    x2[k] = ok ? __ldg(X + (int64_t)c2 * ldx + j) : cmake(0, 0);
-                    x3[k] = ok ? __ldg(X + (int64_t)c3 * ldx + j) : cmake(0, 0);
+                    const bool ok = j < m;   // c < 0: padding entry of the device layout (value 0)
+                    x0[k] = (ok && c0 >= 0) ? __ldg(X + (int64_t)c0 * ldx + j) : cmake(0, 0);
+                    x1[k] = (ok && c1 >= 0) ? __ldg(X + (int64_t)c1 * ldx + j) : cmake(0, 0);
+                    x2[k] = (ok && c2 >= 0) ? __ldg(X + (int64_t)c2 * ldx + j) : cmake(0, 0);
+                    x3[k] = (ok && c3 >= 0) ? __ldg(X + (int64_t)c3 * ldx + j) : cmake(0, 0);
                 }
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
@@ -72,6 +72,7 @@ spmm_csr_kernel(int n, int m, const int* __restrict__ rowptr, const int* __restr
             for (; e < e1; ++e) {
                 const int c0 = __ldg(col + e);
                 const VT v0 = __ldg(val + e);
+                if (c0 < 0) continue;
 #pragma unroll
                 for (int k = 0; k < CPL; ++k) {
                     const int j = g + k * G;
@@ -191,7 +192,7 @@ int spmm_dispatch(feast_ctx* ctx, int n, int m, const int* rowptr, const int* co
 constexpr int kTiledThreads = 512;
 constexpr int kTiledSmemBudget = 115712;   // (233472 B per SM) / 2 CTAs - 1 KB system reservation each
 constexpr int kRowsCap = 192;              // block rows (tile + halo) resident per CTA: 192 x 32 x 16 B = 96 KB
-constexpr int kNnzCap = 704;               // staged nonzeros per tile
+constexpr int kNnzCap = 768;               // staged (padded) nonzeros per tile
 constexpr int kTileMax = 160;              // rows per tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -218,10 +219,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// four consecutive staged values (16-byte aligned: rows are padded to 8 entries)
+__device__ __forceinline__ void load_vals4(const double* p, double (&v)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void load_vals4(const c128* p, c128 (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = p[k];
+}
+
 template <typename VT> struct TiledSmem {
     static constexpr __host__ __device__ size_t xs_bytes(int G) { return (size_t)kRowsCap * G * sizeof(c128); }
-    static constexpr size_t vs_bytes = (size_t)(kNnzCap + 8) * sizeof(VT);
-    static constexpr size_t ls_bytes = (((size_t)(kNnzCap + 8) * sizeof(uint16_t)) + 15) & ~(size_t)15;
+    static constexpr size_t vs_bytes = (size_t)kNnzCap * sizeof(VT);
+    static constexpr size_t ls_bytes = (size_t)kNnzCap * sizeof(uint16_t);
     static constexpr size_t rs_bytes = (size_t)(kTileMax + 4) * sizeof(int);
     static constexpr __host__ __device__ size_t total(int G) { return xs_bytes(G) + vs_bytes + ls_bytes + rs_bytes; }
 };
@@ -237,12 +248,11 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t mbar;
     c128* xs = (c128*)smem_raw;                                                 // [kRowsCap][SW]
-    VT* vs = (VT*)(smem_raw + TiledSmem<VT>::xs_bytes(G));                      // [kNnzCap + 8]
-    uint16_t* ls = (uint16_t*)((unsigned char*)vs + TiledSmem<VT>::vs_bytes);   // [kNnzCap + 8]
+    VT* vs = (VT*)(smem_raw + TiledSmem<VT>::xs_bytes(G));                      // [kNnzCap]
+    uint16_t* ls = (uint16_t*)((unsigned char*)vs + TiledSmem<VT>::vs_bytes);   // [kNnzCap]
     int* rs = (int*)((unsigned char*)ls + TiledSmem<VT>::ls_bytes);             // [kTileMax + 1]
     constexpr int UPW = 32 / G;   // rows per warp
     constexpr int NW = kTiledThreads / 32;
-    constexpr int U = 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane % G, sub = lane / G;
 
@@ -258,10 +268,7 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int r0 = __ldg(t_ptr + tile), rows = __ldg(t_ptr + tile + 1) - r0;
         const int hp = __ldg(t_hptr + tile), nref = rows + __ldg(t_hptr + tile + 1) - hp;   // own rows + halo rows
-        const int e_lo = __ldg(rowptr + r0), e_hi = __ldg(rowptr + r0 + rows);
-        const int ea = e_lo & ~7;                      // 16-byte aligned start of the CSR slice (u16 columns)
-        int eb = e_hi & ~7;                            // bulk part ends here; [eb, e_hi) is copied by threads
-        if (eb < ea) eb = ea;
+        const int ea = __ldg(rowptr + r0), eb = __ldg(rowptr + r0 + rows);   // multiples of 8 (padded rows)
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const int j0 = s * G;
@@ -284,9 +291,8 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
                     if (tid == 64) bulk_g2s(ls, lcol + ea, (uint32_t)(eb - ea) * (uint32_t)sizeof(uint16_t), &mbar);
                 }
                 for (int t = tid; t <= rows; t += kTiledThreads) rs[t] = __ldg(rowptr + r0 + t) - ea;
-                for (int e = eb + tid; e < e_hi; e += kTiledThreads) { ls[e - ea] = lcol[e]; vs[e - ea] = __ldg(val + e); }
+                __syncthreads();   // row pointers visible
             }
-            __syncthreads();   // row pointers / slice tail visible
             mbar_wait(&mbar, phase);
             phase ^= 1u;
 
@@ -294,16 +300,23 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
             for (int lr = warp * UPW + sub; lr < rows; lr += NW * UPW) {
                 const int e0 = rs[lr], e1 = rs[lr + 1];
                 c128 acc = cmake(0.0, 0.0);
-                for (int e = e0; e < e1; e += U) {
-                    c128 xv[U];
+                for (int e = e0; e < e1; e += 8) {
+                    // 8 tile-local columns in one 16-byte broadcast load; 0xFFFF = padding (only at the end of a row)
+                    const uint4 iv = *reinterpret_cast<const uint4*>(ls + e);
+                    const unsigned w[4] = {iv.x, iv.y, iv.z, iv.w};
 #pragma unroll
-                    for (int k = 0; k < U; ++k) {
-                        const int lc = (e + k < e1) ? (int)ls[e + k] : lr;   // padding entries read the own row
-                        xv[k] = xs[(size_t)lc * SW + gg];
+                    for (int h = 0; h < 2; ++h) {
+                        unsigned lc[4];
+                        lc[0] = w[2 * h] & 0xFFFFu; lc[1] = w[2 * h] >> 16; lc[2] = w[2 * h + 1] & 0xFFFFu; lc[3] = w[2 * h + 1] >> 16;
+                        if (lc[0] == 0xFFFFu) break;
+                        c128 xv[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) xv[k] = xs[(size_t)(lc[k] == 0xFFFFu ? (unsigned)lr : lc[k]) * SW + gg];
+                        VT vv[4];
+                        load_vals4(vs + e + 4 * h, vv);   // padding values are 0
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) ValOps<VT>::fma(acc, vv[k], xv[k]);
                     }
-#pragma unroll
-                    for (int k = 0; k < U; ++k)
-                        if (e + k < e1) ValOps<VT>::fma(acc, vs[e + k], xv[k]);
                 }
                 if (g < SW) {
                     Y[(int64_t)(r0 + lr) * ldy + j0 + g] = acc;
@@ -376,7 +389,10 @@ int spmm_tiled_dispatch(feast_ctx* ctx, int m, const VT* val, const c128* X, int
 
 size_t spmm_partials_bytes(int m) { return (size_t)kNumSMs * 8 * 2 * (size_t)(m < 128 ? 128 : m) * sizeof(double); }
 
-TileCaps spmm_tile_caps() { return TileCaps{kRowsCap, kNnzCap, kTileMax}; }
+TileCaps spmm_tile_caps() {
+    static const int domain = getenv("FEAST_TILE_DOMAIN") ? atoi(getenv("FEAST_TILE_DOMAIN")) : 65536;
+    return TileCaps{kRowsCap, kNnzCap, kTileMax, domain};
+}
 
 int launch_spmm(feast_ctx* ctx, int64_t n, int m, const int* rowptr, const int* col, const double* rvals,
                 const c128* cvals, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
@@ -426,7 +442,8 @@ __global__ void scatter_dense_kernel(int n, const int* __restrict__ rowptr, cons
     // one warp per row; Z pre-zeroed
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
-    for (int e = rowptr[warp] + lane; e < rowptr[warp + 1]; e += 32) Z[(int64_t)warp * n + col[e]] = zvals[e];  // row-major
+    for (int e = rowptr[warp] + lane; e < rowptr[warp + 1]; e += 32)
+        if (col[e] >= 0) Z[(int64_t)warp * n + col[e]] = zvals[e];  // row-major; col < 0: padding entry
 }
 
 // R[row, j] = sum_e ( sum_i lam_j^i a_i[e] ) X[col_e, j]   -- one pass over X, Horner per column
@@ -448,6 +465,7 @@ poly_residual_kernel(int n, int m, AsmArgs a, const int* __restrict__ rowptr, co
         for (int k = 0; k < CPL; ++k) acc[k] = cmake(0, 0);
         for (int e = rowptr[row]; e < rowptr[row + 1]; ++e) {
             const int c0 = __ldg(col + e);
+            if (c0 < 0) continue;   // padding entry
             c128 av[FEAST_MAX_SLOTS];
 #pragma unroll
             for (int i = 0; i < FEAST_MAX_SLOTS; ++i) {

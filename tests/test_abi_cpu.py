@@ -134,7 +134,7 @@ def test_tile_plan_is_a_permutation_and_cuts_the_halo(lib):
     for reorder in (0, 1):
         order = np.zeros(n, dtype=np.int32)
         nt, halo = C.c_int(0), C.c_double(0.0)
-        rc = lib.feast_debug_tile_plan(n, _lib.ptr(rowptr), _lib.ptr(col), reorder, 192, 704, 160, _lib.ptr(order),
+        rc = lib.feast_debug_tile_plan(n, _lib.ptr(rowptr), _lib.ptr(col), reorder, 192, 704, 160, 4096 if reorder else 0, _lib.ptr(order),
                                        C.byref(nt), C.byref(halo))
         assert rc == 0
         assert np.array_equal(np.sort(order), np.arange(n))
@@ -146,5 +146,5 @@ def test_tile_plan_is_a_permutation_and_cuts_the_halo(lib):
     D = sp.csr_matrix(np.ones((1, 300)))
     Dfull = sp.vstack([D, sp.csr_matrix((299, 300))]).tocsr()
     rc = lib.feast_debug_tile_plan(300, _lib.ptr(np.ascontiguousarray(Dfull.indptr, dtype=np.int64)),
-                                   _lib.ptr(np.ascontiguousarray(Dfull.indices, dtype=np.int32)), 1, 192, 704, 160, None, None, None)
+                                   _lib.ptr(np.ascontiguousarray(Dfull.indices, dtype=np.int32)), 1, 192, 704, 160, 0, None, None, None)
     assert rc == 1
