@@ -253,6 +253,7 @@ int build_union(feast_ctx* ctx) {
     ctx->reordered = false;
     ctx->tiles_ok = false;
     const TileCaps caps = spmm_tile_caps();
+    ctx->tile_cfg = spmm_tile_cfg();
     TilePlan plan;
     const bool reorder = want_reorder(ctx);
     build_tile_order(n, rowptr.data(), col.data(), reorder, caps, plan);

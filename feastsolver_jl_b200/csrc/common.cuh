@@ -124,6 +124,7 @@ struct feast_ctx {
     bool reordered = false;
     bool tiles_ok = false;        // tile plan usable by the tiled SpMM
     int ntiles = 0;
+    int tile_cfg = 0;             // tile configuration of the plan (spmm.cu TileCfg*)
     int* t_ptr = nullptr;         // [ntiles + 1] first row of each tile
     int* t_hptr = nullptr;        // [ntiles + 1] halo list offsets
     int* t_hidx = nullptr;        // halo rows per tile

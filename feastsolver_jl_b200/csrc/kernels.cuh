@@ -50,6 +50,7 @@ int launch_rowmajor_to_colmajor(feast_ctx* ctx, int64_t n, int m, const c128* sr
 // ---- spmm.cu: capacities of the tiled SpMM (shared-memory rows / staged nonzeros / rows per tile)
 struct TileCaps;
 TileCaps spmm_tile_caps();
+int spmm_tile_cfg();   // tile configuration the capacities belong to (FEAST_TILE_CFG)
 int launch_real_to_complex(feast_ctx* ctx, int64_t count, const double* src, c128* dst);
 int launch_conj(feast_ctx* ctx, int64_t count, const c128* src, c128* dst);  // dst = conj(src), may alias
 // Z(n x n) = sum_i coef[i] * D_i (dense col-major slots; identity slots add coef to the diagonal)

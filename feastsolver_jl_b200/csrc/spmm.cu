@@ -189,11 +189,24 @@ int spmm_dispatch(feast_ctx* ctx, int n, int m, const int* rowptr, const int* co
 //     the inner loop, the memory-level parallelism is the copy engine's, not the register file's;
 //   * L2->SM traffic per SpMM = (1 + halo/rows) reads of X; with the tile ordering ~2.1 instead of ~5.5.
 // 2 CTAs of 512 threads per SM: one computes while the other waits for its copies.
-constexpr int kTiledThreads = 512;
-constexpr int kTiledSmemBudget = 115712;   // (233472 B per SM) / 2 CTAs - 1 KB system reservation each
-constexpr int kRowsCap = 192;              // block rows (tile + halo) resident per CTA: 192 x 32 x 16 B = 96 KB
-constexpr int kNnzCap = 768;               // staged (padded) nonzeros per tile
-constexpr int kTileMax = 160;              // rows per tile
+// Measured alternatives at C2 (n = 1e6, m0 = 64, real values 0.515 ms with this kernel):
+//   * 3 or 4 smaller CTAs per SM (TileCfg2 / TileCfg1): 0.510 / 0.505 ms although the halo grows to 1.45 / 1.68;
+//   * one 1024-thread CTA with a ring of 2..4 tile buffers, copies issued one to three passes ahead: 0.70 .. 1.09 ms;
+//   * the same ring fed by four dedicated producer warps (empty/full mbarriers, no CTA barrier): 0.54 ms with per-row
+//     bulk copies, 0.74 ms with 16-byte cp.async;
+//   * copies + stores alone (products skipped) take 0.36 ms = 3.35 GB through the SM<->L2 fabric at 9.2 TB/s, i.e. the
+//     fabric's ceiling: what is left above it is product time that two CTAs per SM do not hide completely.
+// Tile configurations (FEAST_TILE_CFG): CTAs per SM x threads, block rows (tile + halo) resident per CTA, staged
+// (padded) nonzeros and max rows per tile.  More, smaller CTAs keep more bulk copies in flight per SM (each CTA
+// waits for its whole tile before computing) at the price of a larger halo.  Shared memory: 233472 B per SM,
+// 1 KB reserved per CTA.
+template <int THREADS, int CTAS, int ROWS, int NNZ, int TMAX> struct TileCfg {
+    static constexpr int kThreads = THREADS, kCtas = CTAS, kRowsCap = ROWS, kNnzCap = NNZ, kTileMax = TMAX;
+    static constexpr int kBudget = 233472 / CTAS - 1024;
+};
+typedef TileCfg<512, 2, 192, 768, 160> TileCfg0;   // 96 KB of block rows per CTA
+typedef TileCfg<256, 4, 96, 384, 80> TileCfg1;     // 48 KB
+typedef TileCfg<384, 3, 128, 512, 112> TileCfg2;   // 64 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -229,29 +242,31 @@ __device__ __forceinline__ void load_vals4(const c128* p, c128 (&v)[4]) {
     for (int k = 0; k < 4; ++k) v[k] = p[k];
 }
 
-template <typename VT> struct TiledSmem {
-    static constexpr __host__ __device__ size_t xs_bytes(int G) { return (size_t)kRowsCap * G * sizeof(c128); }
-    static constexpr size_t vs_bytes = (size_t)kNnzCap * sizeof(VT);
-    static constexpr size_t ls_bytes = (size_t)kNnzCap * sizeof(uint16_t);
-    static constexpr size_t rs_bytes = (size_t)(kTileMax + 4) * sizeof(int);
+template <typename VT, typename CFG> struct TiledSmem {
+    static constexpr __host__ __device__ size_t xs_bytes(int G) { return (size_t)CFG::kRowsCap * G * sizeof(c128); }
+    static constexpr size_t vs_bytes = (size_t)CFG::kNnzCap * sizeof(VT);
+    static constexpr size_t ls_bytes = (size_t)CFG::kNnzCap * sizeof(uint16_t);
+    static constexpr size_t rs_bytes = (size_t)(CFG::kTileMax + 4) * sizeof(int);
     static constexpr __host__ __device__ size_t total(int G) { return xs_bytes(G) + vs_bytes + ls_bytes + rs_bytes; }
 };
 
 // G lanes own one row of the slab at a time (one accumulator per lane; up to 8 products in flight).
 // m <= 2*G: the launch covers one or two slabs.
-template <typename VT, int G, bool DOT>
-__global__ void __launch_bounds__(kTiledThreads, 2)
+template <typename VT, int G, bool DOT, typename CFG>
+__global__ void __launch_bounds__(CFG::kThreads, CFG::kCtas)
 spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* __restrict__ t_hptr,
                   const int* __restrict__ t_hidx, const int* __restrict__ rowptr, const uint16_t* __restrict__ lcol,
                   const VT* __restrict__ val, const c128* __restrict__ X, int ldx, c128* __restrict__ Y, int ldy,
-                  double* __restrict__ partials) {
+                  double* __restrict__ partials, int dbg) {
+    // dbg (FEAST_SPMM_DEBUG, timing experiments only): 1 = skip the products, 2 = skip the halo copies, 4 = skip the stores
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t mbar;
     c128* xs = (c128*)smem_raw;                                                 // [kRowsCap][SW]
-    VT* vs = (VT*)(smem_raw + TiledSmem<VT>::xs_bytes(G));                      // [kNnzCap]
-    uint16_t* ls = (uint16_t*)((unsigned char*)vs + TiledSmem<VT>::vs_bytes);   // [kNnzCap]
-    int* rs = (int*)((unsigned char*)ls + TiledSmem<VT>::ls_bytes);             // [kTileMax + 1]
+    VT* vs = (VT*)(smem_raw + TiledSmem<VT, CFG>::xs_bytes(G));                      // [kNnzCap]
+    uint16_t* ls = (uint16_t*)((unsigned char*)vs + TiledSmem<VT, CFG>::vs_bytes);   // [kNnzCap]
+    int* rs = (int*)((unsigned char*)ls + TiledSmem<VT, CFG>::ls_bytes);             // [kTileMax + 1]
     constexpr int UPW = 32 / G;   // rows per warp
+    constexpr int kTiledThreads = CFG::kThreads;
     constexpr int NW = kTiledThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane % G, sub = lane / G;
@@ -267,7 +282,8 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int r0 = __ldg(t_ptr + tile), rows = __ldg(t_ptr + tile + 1) - r0;
-        const int hp = __ldg(t_hptr + tile), nref = rows + __ldg(t_hptr + tile + 1) - hp;   // own rows + halo rows
+        const int hp = __ldg(t_hptr + tile);
+        const int nref = (dbg & 2) ? rows : rows + __ldg(t_hptr + tile + 1) - hp;   // own rows + halo rows
         const int ea = __ldg(rowptr + r0), eb = __ldg(rowptr + r0 + rows);   // multiples of 8 (padded rows)
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -281,7 +297,8 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
                 mbar_expect_tx(&mbar, bytes);
             }
             __syncthreads();   // the previous pass has finished reading shared memory; the barrier is armed
-            for (int t = tid; t < nref; t += kTiledThreads) {
+            // copy t is issued by lane t / NW of warp t % NW: a warp issues its copies one lane at a time
+            for (int t = lane * NW + warp; t < nref; t += kTiledThreads) {
                 const int srow = t < rows ? r0 + t : __ldg(t_hidx + hp + (t - rows));
                 bulk_g2s(xs + (size_t)t * SW, X + (int64_t)srow * ldx + j0, rowbytes, &mbar);
             }
@@ -300,7 +317,7 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
             for (int lr = warp * UPW + sub; lr < rows; lr += NW * UPW) {
                 const int e0 = rs[lr], e1 = rs[lr + 1];
                 c128 acc = cmake(0.0, 0.0);
-                for (int e = e0; e < e1; e += 8) {
+                for (int e = (dbg & 1) ? e1 : e0; e < e1; e += 8) {
                     // 8 tile-local columns in one 16-byte broadcast load; 0xFFFF = padding (only at the end of a row)
                     const uint4 iv = *reinterpret_cast<const uint4*>(ls + e);
                     const unsigned w[4] = {iv.x, iv.y, iv.z, iv.w};
@@ -318,7 +335,7 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
                         for (int k = 0; k < 4; ++k) ValOps<VT>::fma(acc, vv[k], xv[k]);
                     }
                 }
-                if (g < SW) {
+                if (g < SW && !(dbg & 4)) {
                     Y[(int64_t)(r0 + lr) * ldy + j0 + g] = acc;
                     if (DOT) cfma(dacc[s], xs[(size_t)lr * SW + g], acc);
                 }
@@ -345,53 +362,78 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
     }
 }
 
-template <typename VT, int G>
+template <typename VT, int G, typename CFG>
 int spmm_tiled_launch(feast_ctx* ctx, int m, const VT* val, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
-    const size_t smem = TiledSmem<VT>::total(G) < 16384 ? 16384 : TiledSmem<VT>::total(G);
-    static_assert(TiledSmem<VT>::total(32) <= (size_t)kTiledSmemBudget, "tile does not fit 2 CTAs per SM");
+    const size_t smem = TiledSmem<VT, CFG>::total(G) < 16384 ? 16384 : TiledSmem<VT, CFG>::total(G);
+    static_assert(TiledSmem<VT, CFG>::total(32) <= (size_t)CFG::kBudget, "tile does not fit the CTAs-per-SM target");
     const int ntiles = ctx->ntiles;
-    const int grid = ntiles < 2 * kNumSMs ? ntiles : 2 * kNumSMs;
+    const int grid = ntiles < CFG::kCtas * kNumSMs ? ntiles : CFG::kCtas * kNumSMs;
     static bool attr_done_dot[64] = {}, attr_done[64] = {};   // per device (function attributes are per context)
     const int dev = ctx->device & 63;
+    static const int dbg = getenv("FEAST_SPMM_DEBUG") ? atoi(getenv("FEAST_SPMM_DEBUG")) : 0;
     if (dot_out) {
-        auto kern = spmm_tiled_kernel<VT, G, true>;
+        auto kern = spmm_tiled_kernel<VT, G, true, CFG>;
         if (!attr_done_dot[dev]) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmemBudget));
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kBudget));
             attr_done_dot[dev] = true;
         }
-        kern<<<grid, kTiledThreads, smem, ctx->stream>>>(m, ntiles, ctx->t_ptr, ctx->t_hptr, ctx->t_hidx, ctx->u_rowptr, ctx->u_lcol,
-                                                          val, X, ldx, Y, ldy, ctx->red_d);
+        kern<<<grid, CFG::kThreads, smem, ctx->stream>>>(m, ntiles, ctx->t_ptr, ctx->t_hptr, ctx->t_hidx, ctx->u_rowptr, ctx->u_lcol,
+                                                          val, X, ldx, Y, ldy, ctx->red_d, dbg);
         KLAUNCH_CHECK(ctx);
         reduce_partials_kernel<<<ceil_div(2 * m * 32, 128), 128, 0, ctx->stream>>>(ctx->red_d, grid, 2 * m, (double*)dot_out);
         KLAUNCH_CHECK(ctx);
     } else {
-        auto kern = spmm_tiled_kernel<VT, G, false>;
+        auto kern = spmm_tiled_kernel<VT, G, false, CFG>;
         if (!attr_done[dev]) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTiledSmemBudget));
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kBudget));
             attr_done[dev] = true;
         }
-        kern<<<grid, kTiledThreads, smem, ctx->stream>>>(m, ntiles, ctx->t_ptr, ctx->t_hptr, ctx->t_hidx, ctx->u_rowptr, ctx->u_lcol,
-                                                          val, X, ldx, Y, ldy, nullptr);
+        kern<<<grid, CFG::kThreads, smem, ctx->stream>>>(m, ntiles, ctx->t_ptr, ctx->t_hptr, ctx->t_hidx, ctx->u_rowptr, ctx->u_lcol,
+                                                          val, X, ldx, Y, ldy, nullptr, dbg);
         KLAUNCH_CHECK(ctx);
     }
     return 0;
 }
 
+template <typename VT, typename CFG>
+int spmm_tiled_dispatch_g(feast_ctx* ctx, int m, const VT* val, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
+    if (m <= 4) return spmm_tiled_launch<VT, 4, CFG>(ctx, m, val, X, ldx, Y, ldy, dot_out);
+    if (m <= 8) return spmm_tiled_launch<VT, 8, CFG>(ctx, m, val, X, ldx, Y, ldy, dot_out);
+    if (m <= 16) return spmm_tiled_launch<VT, 16, CFG>(ctx, m, val, X, ldx, Y, ldy, dot_out);
+    return spmm_tiled_launch<VT, 32, CFG>(ctx, m, val, X, ldx, Y, ldy, dot_out);   // m <= 64: one or two slabs of 32 columns
+}
+
+int tile_cfg_setting() {
+    static const int cfg = [] {
+        const char* e = getenv("FEAST_TILE_CFG");
+        const int v = e ? atoi(e) : 0;
+        return (v < 0 || v > 2) ? 0 : v;
+    }();
+    return cfg;
+}
+
 template <typename VT>
 int spmm_tiled_dispatch(feast_ctx* ctx, int m, const VT* val, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
-    if (m <= 4) return spmm_tiled_launch<VT, 4>(ctx, m, val, X, ldx, Y, ldy, dot_out);
-    if (m <= 8) return spmm_tiled_launch<VT, 8>(ctx, m, val, X, ldx, Y, ldy, dot_out);
-    if (m <= 16) return spmm_tiled_launch<VT, 16>(ctx, m, val, X, ldx, Y, ldy, dot_out);
-    return spmm_tiled_launch<VT, 32>(ctx, m, val, X, ldx, Y, ldy, dot_out);   // m <= 64: one or two slabs of 32 columns
+    switch (ctx->tile_cfg) {
+        case 1: return spmm_tiled_dispatch_g<VT, TileCfg1>(ctx, m, val, X, ldx, Y, ldy, dot_out);
+        case 2: return spmm_tiled_dispatch_g<VT, TileCfg2>(ctx, m, val, X, ldx, Y, ldy, dot_out);
+        default: return spmm_tiled_dispatch_g<VT, TileCfg0>(ctx, m, val, X, ldx, Y, ldy, dot_out);
+    }
 }
 
 }  // namespace
 
 size_t spmm_partials_bytes(int m) { return (size_t)kNumSMs * 8 * 2 * (size_t)(m < 128 ? 128 : m) * sizeof(double); }
 
+int spmm_tile_cfg() { return tile_cfg_setting(); }
+
 TileCaps spmm_tile_caps() {
     static const int domain = getenv("FEAST_TILE_DOMAIN") ? atoi(getenv("FEAST_TILE_DOMAIN")) : 65536;
-    return TileCaps{kRowsCap, kNnzCap, kTileMax, domain};
+    switch (tile_cfg_setting()) {
+        case 1: return TileCaps{TileCfg1::kRowsCap, TileCfg1::kNnzCap, TileCfg1::kTileMax, domain};
+        case 2: return TileCaps{TileCfg2::kRowsCap, TileCfg2::kNnzCap, TileCfg2::kTileMax, domain};
+        default: return TileCaps{TileCfg0::kRowsCap, TileCfg0::kNnzCap, TileCfg0::kTileMax, domain};
+    }
 }
 
 int launch_spmm(feast_ctx* ctx, int64_t n, int m, const int* rowptr, const int* col, const double* rvals,
