@@ -236,6 +236,7 @@ def run_ours(args):
     ctx.set_node_owners(owners)
     ctx.set_solver(**solver_opts)
     ctx.set_subspace(X0)
+    layout = ctx.layout_info()
 
     for _ in range(args.warmup):
         outer_iteration(fs, ctx, contour)
@@ -312,7 +313,9 @@ def run_ours(args):
                                f"nnz={A.nnz}), lowest slice ({cnt} eigenvalues), m0={M0}, {NODES} Gauss-Legendre nodes "
                                f"sharded over {world} GPU(s); step = one outer FEAST iteration ({NODES} node solves + RR)",
                    "inner_solver": f"pseudo-block COCG, rel tol {INNER_TOL}", "l2_policy": "inputs (5 GB of Krylov blocks) exceed the 126 MB L2",
-                   "node_owners": [int(o) for o in owners]},
+                   "node_owners": [int(o) for o in owners],
+                   "layout": {"rows_renumbered": layout["reordered"], "spmm_tiles": layout["ntiles"],
+                              "halo_rows_per_row": round(layout["halo_rows_per_row"], 3)}},
         "time_to_solution_s": tts, "outer_iterations": len(st_e2e["history"]), "eigenvalues_found": int(e.size),
         "eigenvalues_exact": int(exact.size), "max_residual": float(rs.max()) if rs.size else None,
         "eig_rel_err_vs_analytic": eig_err, "inner_iters_per_step": inner_total / args.steps,
@@ -321,7 +324,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(d2h / max(1, iters_with_solves)), "time_to_solution_s": tts,
                 "api": "feastsolver_jl_b200.gen_feast(X, A, B, contour) with host numpy/scipy buffers, to convergence"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "spmm_csr_kernel<c128> (COCG q = (A - zB) p, fused <p,q>)", "bound": "hbm",
+        "roofline": {"kernel": "spmm_tiled_kernel<c128, DOT> (COCG q = (A - zB) p, fused <p,q>)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "bytes_per_launch": bytes_per_launch, "ms_per_launch": spmm_ms,
