@@ -610,7 +610,13 @@ int solve_shifted(feast_ctx* ctx, int solver, int method, int k, const hc128* co
             if (info && !st.info) st.info = info;
         }
         if (e1) cudaEventRecord(e1, ctx->stream);
-        FEAST_TRY(band_solve(ctx, *bf, ctx->zvals, m, rhs, Y));
+        FEAST_TRY(ensure_block(ctx, ctx->W2));
+        int steps = 0;
+        double rel = 0.0;
+        FEAST_TRY(band_solve_refined(ctx, *bf, ctx->zvals, m, rhs, Y, ctx->W2.p, &steps, &rel));
+        st.inner_iters_total += steps;                                  // refinement steps
+        st.inner_iters_max = std::max(st.inner_iters_max, steps);
+        st.inner_relres_max = std::max(st.inner_relres_max, rel);
     } else {
         FEAST_TRY(assemble_sparse_Z(ctx, coef, ctx->zvals));
         if (e1) cudaEventRecord(e1, ctx->stream);
@@ -1451,7 +1457,7 @@ int feast_solve(feast_ctx* ctx, const feast_factor* F, int64_t n, int nrhs, cons
         FEAST_TRY(dense_getrs(ctx, n, F->lu.lu, F->lu.perm, F->lu.dinv, m, rhs, ctx->W1.p, conj_transpose != 0));
     } else if (F->kind == FEAST_SOLVER_BANDED_LU) {
         if (conj_transpose) return feast_fail(ctx, FEAST_ERR_STATE, "adjoint solves are not available with the banded solver");
-        FEAST_TRY(band_solve(ctx, F->band, F->zvals, m, rhs, ctx->W1.p));
+        FEAST_TRY(band_solve_refined(ctx, F->band, F->zvals, m, rhs, ctx->W1.p, ctx->W2.p, nullptr, nullptr));
     } else {
         if (conj_transpose && !F->symmetric)
             return feast_fail(ctx, FEAST_ERR_STATE, "adjoint Krylov solve needs a symmetric operator in this build");

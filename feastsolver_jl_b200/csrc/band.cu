@@ -6,6 +6,9 @@
 // Every O(b^3) step is the dense machinery of dense.cu (cooperative panel LU + DMMA ZGEMM); the
 // off-diagonal blocks are scattered from the sparse values on the fly and never stored.
 // Replaces sparse `lu` + `ldiv!` (UMFPACK upstream) for src/nlfeast.jl:17-28,36-61 at C4 scale.
+#include <cmath>
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace {
@@ -37,6 +40,15 @@ __global__ void copy_pad_kernel(int b, int m, int rows, const c128* __restrict__
 __global__ void sub_rows_kernel(int m, int rows, const c128* __restrict__ a, const c128* __restrict__ s, c128* __restrict__ dst) {
     const int total = rows * m;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) dst[t] = csub(a[t], s[t]);
+}
+
+// r = b - r
+__global__ void residual_inplace_kernel(int64_t total, const c128* __restrict__ b, c128* __restrict__ r) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) r[t] = csub(b[t], r[t]);
+}
+// y += d
+__global__ void add_inplace_kernel(int64_t total, c128* __restrict__ y, const c128* __restrict__ d) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) y[t] = cadd(y[t], d[t]);
 }
 
 int scatter_block(feast_ctx* ctx, int b, int I, int J, const c128* zvals, c128* dst) {
@@ -154,5 +166,46 @@ int band_solve(feast_ctx* ctx, const BandFactor& F, const c128* zvals, int m, co
         KLAUNCH_CHECK(ctx);
         CUDA_TRY(ctx, cudaMemcpyAsync(t_prev, Y + (size_t)I * b * m, sizeof(c128) * (size_t)b * m, cudaMemcpyDeviceToDevice, ctx->stream));
     }
+    return 0;
+}
+
+// Solve with iterative refinement against the assembled sparse operator: recovers the digits the elimination loses
+// when a Schur complement S_I is ill-conditioned while the shifted operator itself is not (pivoting happens inside
+// the S_I only).  A step costs one SpMM and one more pair of sweeps with the same factors; it stops as soon as the
+// residual no longer contracts -- which is immediately for the numerically singular operators of C4 at n = 250 000
+// (cond >> 1e16: the elimination is backward stable there, see profiles/r1b_c4_full_n250000.json).  work: n x m scratch.
+int band_solve_refined(feast_ctx* ctx, const BandFactor& F, const c128* zvals, int m, const c128* Rhs, c128* Y, c128* work,
+                       int* steps_out, double* relres_out) {
+    const int64_t n = ctx->n, total = n * m;
+    FEAST_TRY(band_solve(ctx, F, zvals, m, Rhs, Y));
+    double* bn2 = (double*)(ctx->small_d + (size_t)4 * ctx->m0 * ctx->m0);
+    double* rn2 = bn2 + m;
+    double* h = (double*)ctx->pinned;
+    FEAST_TRY(launch_colnorm2(ctx, n, m, Rhs, bn2));
+    const int eg = 148 * 8;
+    const int max_steps = 4;
+    double prev = 0.0, rel = 0.0;
+    int steps = 0;
+    for (int it = 0; it <= max_steps; ++it) {
+        FEAST_TRY(launch_spmm(ctx, n, m, ctx->u_rowptr, ctx->u_col, nullptr, zvals, Y, m, work, m, nullptr));
+        residual_inplace_kernel<<<eg, 256, 0, ctx->stream>>>(total, Rhs, work);
+        KLAUNCH_CHECK(ctx);
+        FEAST_TRY(launch_colnorm2(ctx, n, m, work, rn2));
+        CUDA_TRY(ctx, cudaMemcpyAsync(h, bn2, sizeof(double) * 2 * m, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        rel = 0.0;
+        for (int j = 0; j < m; ++j)
+            if (h[j] > 0.0) rel = std::max(rel, std::sqrt(h[m + j] / h[j]));
+        if (!(rel == rel)) break;                                 // NaN: leave the plain solution
+        if (rel <= 1e-14 || it == max_steps) break;
+        if (it > 0 && rel > 0.25 * prev) break;                    // no longer contracting
+        prev = rel;
+        FEAST_TRY(band_solve(ctx, F, zvals, m, work, work));       // correction, in place
+        add_inplace_kernel<<<eg, 256, 0, ctx->stream>>>(total, Y, work);
+        KLAUNCH_CHECK(ctx);
+        ++steps;
+    }
+    if (steps_out) *steps_out = steps;
+    if (relres_out) *relres_out = rel;
     return 0;
 }

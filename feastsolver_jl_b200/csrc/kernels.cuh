@@ -83,6 +83,9 @@ struct BandFactor;
 int band_factor(feast_ctx* ctx, const c128* zvals, BandFactor& F, int* info);
 int band_solve(feast_ctx* ctx, const BandFactor& F, const c128* zvals, int m, const c128* Rhs, c128* Y);
 void band_free(BandFactor& F);
+// band_solve + iterative refinement against the assembled sparse operator (work: n x m scratch)
+int band_solve_refined(feast_ctx* ctx, const BandFactor& F, const c128* zvals, int m, const c128* Rhs, c128* Y, c128* work,
+                       int* steps_out, double* relres_out);
 int dense_build_diag_inverses(feast_ctx* ctx, int64_t n, const c128* LU, c128* dinv);
 int dense_build_perm(feast_ctx* ctx, int64_t n, const int* ipiv_d, int* perm_d);
 size_t spmm_partials_bytes(int m);
