@@ -8,13 +8,12 @@
 
 typedef std::complex<double> hc128;
 
-// Cholesky G = R^H R (R upper) of a Hermitian matrix with UNIT-scaled diagonal, clamping
-// pivots at tau: any positive value in place of an unreliable pivot keeps the identity
-// V_old = V_new R exact and only affects orthonormality of V_new, which the next
-// pass repairs (iterated Cholesky-QR).  Returns the number of clamped pivots.
-inline int chol_upper_clamped(int m, const std::vector<hc128>& G, std::vector<hc128>& R, double tau) {
+// Cholesky G = R^H R (R upper) of a Hermitian matrix (column-major).  Returns false when a pivot is not
+// safely positive (<= min_pivot); the pivot is then replaced by min_pivot so that R stays finite, but the
+// caller should not use such a factor (see orthonormalize in api.cu: it retries with a shifted matrix).
+inline bool chol_upper(int m, const std::vector<hc128>& G, std::vector<hc128>& R, double min_pivot) {
     R.assign((size_t)m * m, hc128(0, 0));
-    int clamped = 0;
+    bool ok = true;
     for (int j = 0; j < m; ++j) {
         for (int i = 0; i < j; ++i) {
             hc128 s = G[(size_t)j * m + i];  // G(i,j)
@@ -23,10 +22,10 @@ inline int chol_upper_clamped(int m, const std::vector<hc128>& G, std::vector<hc
         }
         double d = G[(size_t)j * m + j].real();
         for (int k = 0; k < j; ++k) d -= std::norm(R[(size_t)j * m + k]);
-        if (!(d > tau)) { d = tau; ++clamped; }
+        if (!(d > min_pivot)) { d = min_pivot; ok = false; }
         R[(size_t)j * m + j] = hc128(std::sqrt(d), 0.0);
     }
-    return clamped;
+    return ok;
 }
 
 // inverse of an upper-triangular matrix (column-major)
