@@ -185,5 +185,23 @@ extern "C" FEAST_API int feast_debug_tile_plan(int64_t n, const int64_t* rowptr,
     if (order) for (int64_t i = 0; i < n; ++i) order[i] = plan.order[i];
     if (ntiles) *ntiles = (int)plan.tile_ptr.size() - 1;
     if (halo_ratio) *halo_ratio = plan.halo_ratio;
+    // self-check of the layout the tiled SpMM consumes: every tile respects the capacities and every tile-local
+    // column number maps back (own rows, then the halo list) to the column of the permuted pattern
+    const int nt = (int)plan.tile_ptr.size() - 1;
+    for (int t = 0; t < nt && plan.ok; ++t) {
+        const int r0 = plan.tile_ptr[t], r1 = plan.tile_ptr[t + 1], rows = r1 - r0;
+        const int h0 = plan.halo_ptr[t], nh = plan.halo_ptr[t + 1] - h0;
+        if (rows < 1 || rows > tile_max || rows + nh > rows_cap) return 2;
+        int64_t nnzp = 0;
+        for (int i = r0; i < r1; ++i) {
+            nnzp += (rp[i + 1] - rp[i] + 7) & ~(int64_t)7;
+            for (int64_t e = rp[i]; e < rp[i + 1]; ++e) {
+                const int lc = lcol[(size_t)e];
+                const int back = lc < rows ? r0 + lc : (lc - rows < nh ? plan.halo_idx[h0 + lc - rows] : -1);
+                if (back != cp[e]) return 3;
+            }
+        }
+        if (nnzp > nnz_cap) return 2;
+    }
     return plan.ok ? 0 : 1;
 }

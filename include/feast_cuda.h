@@ -203,7 +203,8 @@ FEAST_API int  feast_phase_times(feast_ctx* ctx, double* ms3, int reset);
  * fetched from outside a tile per row.  Blocks cross the ABI in the caller's ordering.          */
 FEAST_API int  feast_layout_info(const feast_ctx* ctx, int* info4, double* halo);
 /* Host-only (no device): the tile plan the library would build for a 0-based CSR pattern with the
- * given capacities; order[i_new] = i_old (may be NULL).  Returns 1 if a single row exceeds them. */
+ * given capacities; order[i_new] = i_old (may be NULL).  Returns 1 if a single row exceeds them,
+ * 2 / 3 if the plan fails its self-check (capacities / tile-local column numbers).              */
 FEAST_API int  feast_debug_tile_plan(int64_t n, const int64_t* rowptr, const int* col, int reorder, int rows_cap,
                                      int nnz_cap, int tile_max, int domain_rows, int* order, int* ntiles,
                                      double* halo_ratio);

@@ -148,3 +148,35 @@ def test_tile_plan_is_a_permutation_and_cuts_the_halo(lib):
     rc = lib.feast_debug_tile_plan(300, _lib.ptr(np.ascontiguousarray(Dfull.indptr, dtype=np.int64)),
                                    _lib.ptr(np.ascontiguousarray(Dfull.indices, dtype=np.int32)), 1, 192, 704, 160, 0, None, None, None)
     assert rc == 1
+
+
+@pytest.mark.parametrize("kind", ["lap2d_nonsym", "random_sparse", "dense_band"])
+def test_tile_plan_self_check_on_irregular_patterns(lib, kind):
+    """The plan builder's self-check (capacities respected, every 16-bit tile-local column maps back to the permuted
+    global column) on patterns that are not grid-like: non-symmetric, random, and a wide band."""
+    import ctypes as C
+    import scipy.sparse as sp
+    from feastsolver_jl_b200 import _lib
+    rng = np.random.default_rng(3)
+    if kind == "lap2d_nonsym":
+        m = 40
+        K = sp.diags([-1.0, 2.0, -0.5], [-1, 0, 1], shape=(m, m))
+        A = (sp.kron(K, sp.identity(m)) + sp.kron(sp.identity(m), K)).tocsr()
+    elif kind == "random_sparse":
+        A = (sp.random(3000, 3000, density=0.002, random_state=5) + sp.identity(3000)).tocsr()
+    else:
+        n = 1500
+        A = sp.diags([rng.standard_normal(n - abs(o)) for o in range(-20, 21)], list(range(-20, 21))).tocsr()
+    A.sort_indices()
+    n = A.shape[0]
+    rowptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+    col = np.ascontiguousarray(A.indices, dtype=np.int32)
+    for reorder in (0, 1):
+        for caps in ((192, 768, 160, 0), (96, 384, 80, 512)):
+            order = np.zeros(n, dtype=np.int32)
+            nt, halo = C.c_int(0), C.c_double(0.0)
+            rc = lib.feast_debug_tile_plan(n, _lib.ptr(rowptr), _lib.ptr(col), reorder, caps[0], caps[1], caps[2], caps[3],
+                                           _lib.ptr(order), C.byref(nt), C.byref(halo))
+            assert rc == 0, (kind, reorder, caps, rc)
+            assert np.array_equal(np.sort(order), np.arange(n))
+            assert nt.value >= -(-n // caps[2])
