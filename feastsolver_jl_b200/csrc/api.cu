@@ -461,7 +461,7 @@ int orthonormalize(feast_ctx* ctx, BlockVec& V, std::vector<hc128>* Rtot_out) {
     const int m = ctx->m0;
     FEAST_TRY(ensure_block(ctx, ctx->W1));
     FEAST_TRY(ensure_pinned(ctx, sizeof(hc128) * (size_t)m * m + 256));
-    std::vector<hc128> G((size_t)m * m), Gs, R, Ri, Rtot, tmp;
+    std::vector<hc128> G((size_t)m * m), Ri, RD, Rtot, tmp;
     if (Rtot_out) {
         Rtot.assign((size_t)m * m, hc128(0, 0));
         for (int j = 0; j < m; ++j) Rtot[(size_t)j * m + j] = 1.0;
@@ -469,47 +469,20 @@ int orthonormalize(feast_ctx* ctx, BlockVec& V, std::vector<hc128>* Rtot_out) {
     c128* G_d = ctx->small_d;
     c128* M_d = ctx->small_d + (size_t)m * m;
     const int maxpass = 10;
-    const double u = 1.1e-16;
-    const double shift = 11.0 * ((double)m * (double)n + (double)m * (m + 1.0)) * u * (double)m;   // ||V D^-1||_2^2 <= m
+    double prev_err = -1.0;
     for (int pass = 0; pass < maxpass; ++pass) {
         FEAST_TRY(launch_gram(ctx, n, m, V.p, V.p, G_d));
         CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, G_d, sizeof(c128) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         memcpy(G.data(), ctx->pinned, sizeof(hc128) * m * m);
-        std::vector<double> d(m);
-        for (int j = 0; j < m; ++j) {
-            const double g = G[(size_t)j * m + j].real();
-            d[j] = (g > 0.0 && std::isfinite(g)) ? std::sqrt(g) : 1.0;
-        }
-        double dev = 0.0;
-        for (int j = 0; j < m; ++j)
-            for (int i = 0; i < m; ++i) {
-                hc128 g = G[(size_t)j * m + i] / (d[i] * d[j]);
-                G[(size_t)j * m + i] = g;
-                dev = std::max(dev, std::abs(g - (i == j ? hc128(1, 0) : hc128(0, 0))));
-            }
-        bool scaled_only = true;
-        for (int j = 0; j < m; ++j) if (std::fabs(d[j] - 1.0) > 4e-16) scaled_only = false;
-        if (dev <= 8e-16 * std::sqrt((double)m) + 4e-16 && scaled_only) break;  // orthonormal to rounding
-        bool ok = false;
-        if (dev < 0.5) ok = chol_upper(m, G, R, shift);   // a pivot below the shift level: not safely positive definite
-        if (!ok || !std::isfinite(dev)) {
-            Gs = G;
-            for (int j = 0; j < m; ++j) Gs[(size_t)j * m + j] += shift;
-            chol_upper(m, Gs, R, 0.5 * shift);
-        }
-        triu_inverse(m, R, Ri);
+        if (cholqr_pass(m, (double)n, G, Ri, RD, prev_err)) break;               // orthonormal to rounding (host_small.h)
         // V_new = V * D^-1 * R^-1
-        for (int j = 0; j < m; ++j)
-            for (int i = 0; i < m; ++i) Ri[(size_t)j * m + i] /= d[i];
         CUDA_TRY(ctx, cudaMemcpyAsync(M_d, Ri.data(), sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
         FEAST_TRY(launch_update(ctx, n, m, V.p, M_d, ctx->W1.p));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // Ri is a host temporary
         std::swap(V.p, ctx->W1.p);
         if (Rtot_out) {  // Rtot <- R * D * Rtot
-            for (int j = 0; j < m; ++j)
-                for (int i = 0; i < m; ++i) R[(size_t)j * m + i] *= d[j];
-            matmul_small(m, R, Rtot, tmp);
+            matmul_small(m, RD, Rtot, tmp);
             Rtot.swap(tmp);
         }
     }

@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "../../include/feast_cuda.h"
+#include "host_small.h"
 
 // Greedy growth of tiles.  dom (optional): vertex -> domain; tiles never cross a domain boundary and the domains
 // are swept one after the other (dom_list holds the vertices grouped by domain, dom_ptr the group offsets).
@@ -204,4 +205,41 @@ extern "C" FEAST_API int feast_debug_tile_plan(int64_t n, const int64_t* rowptr,
         if (nnzp > nnz_cap) return 2;
     }
     return plan.ok ? 0 : 1;
+}
+
+// Host-only restatement of orthonormalize() (api.cu) for CPU regression tests: the same pass logic (host_small.h
+// cholqr_pass) with the Gram matrix and the block update computed on the host.  V: n x m column-major, overwritten
+// with the orthonormal factor; Rtot (m x m column-major): V_in = V_out * Rtot.
+extern "C" FEAST_API int feast_debug_cholqr(int64_t n, int m, feast_c128* V, int64_t ldv, feast_c128* Rtot_out, int* passes) {
+    if (n < 1) return -1;
+    if (m < 1 || m > n) return -2;
+    if (!V) return -3;
+    if (ldv < n) return -4;
+    hc128* Vc = reinterpret_cast<hc128*>(V);
+    std::vector<hc128> G((size_t)m * m), Ri, RD, Rtot((size_t)m * m, hc128(0, 0)), tmp, row(m);
+    for (int j = 0; j < m; ++j) Rtot[(size_t)j * m + j] = 1.0;
+    int pass = 0;
+    double prev_err = -1.0;
+    for (; pass < 10; ++pass) {
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < m; ++i) {
+                hc128 s(0, 0);
+                for (int64_t r = 0; r < n; ++r) s += std::conj(Vc[(size_t)i * ldv + r]) * Vc[(size_t)j * ldv + r];
+                G[(size_t)j * m + i] = s;
+            }
+        if (cholqr_pass(m, (double)n, G, Ri, RD, prev_err)) break;
+        for (int64_t r = 0; r < n; ++r) {       // V_new = V * Ri, row by row
+            for (int j = 0; j < m; ++j) {
+                hc128 s(0, 0);
+                for (int k = 0; k <= j; ++k) s += Vc[(size_t)k * ldv + r] * Ri[(size_t)j * m + k];
+                row[j] = s;
+            }
+            for (int j = 0; j < m; ++j) Vc[(size_t)j * ldv + r] = row[j];
+        }
+        matmul_small(m, RD, Rtot, tmp);
+        Rtot.swap(tmp);
+    }
+    if (Rtot_out) for (size_t t = 0; t < (size_t)m * m; ++t) { Rtot_out[t].re = Rtot[t].real(); Rtot_out[t].im = Rtot[t].imag(); }
+    if (passes) *passes = pass;
+    return 0;
 }

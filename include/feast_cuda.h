@@ -208,6 +208,10 @@ FEAST_API int  feast_layout_info(const feast_ctx* ctx, int* info4, double* halo)
 FEAST_API int  feast_debug_tile_plan(int64_t n, const int64_t* rowptr, const int* col, int reorder, int rows_cap,
                                      int nnz_cap, int tile_max, int domain_rows, int* order, int* ntiles,
                                      double* halo_ratio);
+/* Host-only restatement of the library's orthonormalisation (iterated, shifted Cholesky-QR; replaces
+ * `qr(Q).Q`, src/feast.jl:41, and the tall `svd!(Q0)` of src/utils.jl:70) for CPU regression tests:
+ * V (n x m column-major, ldv) is overwritten with the orthonormal factor, V_in = V_out * Rtot.     */
+FEAST_API int  feast_debug_cholqr(int64_t n, int m, feast_c128* V, int64_t ldv, feast_c128* Rtot, int* passes);
 
 #ifdef __cplusplus
 }

@@ -180,3 +180,48 @@ def test_tile_plan_self_check_on_irregular_patterns(lib, kind):
             assert rc == 0, (kind, reorder, caps, rc)
             assert np.array_equal(np.sort(order), np.arange(n))
             assert nt.value >= -(-n // caps[2])
+
+
+def _cholqr(lib, V):
+    import ctypes as C
+    from feastsolver_jl_b200 import _lib
+    n, m = V.shape
+    Vf = np.asfortranarray(V, dtype=np.complex128).copy(order="F")
+    R = np.zeros((m, m), dtype=np.complex128, order="F")
+    passes = C.c_int(0)
+    rc = lib.feast_debug_cholqr(n, m, _lib.ptr(Vf), n, _lib.ptr(R), C.byref(passes))
+    assert rc == 0
+    return Vf, R, passes.value
+
+
+def test_cholqr_regression_filtered_feast_block(lib):
+    """Host side of the orthonormalisation (host_small.h cholqr_pass, shared with the device path): the block that broke
+    the first (clamped-pivot) version -- the accumulator Q0 of an emulated nlfeast pass, singular values 3.7 ... 1e-9 --
+    must come back orthonormal with V_in = V_out * Rtot to rounding (the old version: reconstruction error 5e17)."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "cholqr_failing_block.npz"))
+    R0 = d["R0"]
+    rng = np.random.default_rng(11)
+    n, m = 1500, R0.shape[0]
+    Q, _ = np.linalg.qr(rng.standard_normal((n, m)) + 1j * rng.standard_normal((n, m)))
+    V = Q @ R0
+    U, R, passes = _cholqr(lib, V)
+    assert passes <= 6
+    assert np.abs(U.conj().T @ U - np.eye(m)).max() < 5e-15
+    assert np.abs(U @ R - V).max() <= 1e-13 * np.abs(V).max()
+    # the small singular values survive in Rtot (Beyn's step divides by them, src/utils.jl:73)
+    s_true = np.linalg.svd(R0, compute_uv=False)
+    s_got = np.linalg.svd(R, compute_uv=False)
+    assert np.abs(s_got - s_true).max() <= 1e-13 * s_true[0]
+
+
+@pytest.mark.parametrize("cond", [1e3, 1e9, 1e15, 0.0])
+def test_cholqr_ill_conditioned_and_rank_deficient(lib, cond):
+    rng = np.random.default_rng(5)
+    n, m = 1200, 24
+    U0, _ = np.linalg.qr(rng.standard_normal((n, m)) + 1j * rng.standard_normal((n, m)))
+    W0, _ = np.linalg.qr(rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m)))
+    sv = np.logspace(0, -np.log10(cond), m) if cond > 0 else np.concatenate([np.ones(m - 5), np.zeros(5)])
+    V = (U0 * sv[None, :]) @ W0.conj().T
+    U, R, passes = _cholqr(lib, V)
+    assert np.abs(U.conj().T @ U - np.eye(m)).max() < 5e-15
+    assert np.abs(U @ R - V).max() <= 1e-13 * np.abs(V).max()
