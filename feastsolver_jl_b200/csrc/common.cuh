@@ -88,6 +88,12 @@ struct BandFactor {          // block-tridiagonal LU of a banded operator (band.
     c128* lu = nullptr;      // [nbk][b*b] row-major LU of S_I
     int* piv = nullptr;      // [nbk][2*b] ipiv then perm
     c128* dinv = nullptr;    // [nbk][2*b*kDiagNB] diagonal-block inverses of each S_I
+    // pivoted variant (band_factor_pivoted: partial pivoting across adjacent block rows, EXPERIMENTAL, FEAST_BAND_PIVOT=1):
+    // lu = [nbk][b*b] L11\U11 of each 2b x b panel (last block: LU of the final Schur complement), piv = [nbk][2*b]
+    // (window-relative interchanges, then the perm of the last block)
+    bool pivoted = false;
+    c128* l21 = nullptr;     // [nbk][b*b] multipliers of the lower half of each panel
+    c128* u12 = nullptr;     // [nbk][b*2b] row-major (ld 2b): the U rows of block columns I+1, I+2
 };
 
 struct feast_factor {        // fine-grained plugin handle

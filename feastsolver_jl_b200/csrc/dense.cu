@@ -274,7 +274,7 @@ int trsm_rec(feast_ctx* ctx, int h, int ncols, const c128* T, int64_t sTi, int64
     return 0;
 }
 
-int lu_panel(feast_ctx* ctx, int64_t n, c128* Z, int64_t lda, int j0, int w, int* ipiv, LUWork& wk) {
+int lu_panel(feast_ctx* ctx, int64_t n, c128* Z, int64_t lda, int j0, int w, int* ipiv, LUWork& wk, int64_t ncols) {
     PanelArgs a;
     a.A = Z + (int64_t)j0 * lda + j0;   // row-major: (row j0, col j0)
     a.lda = lda;
@@ -300,19 +300,19 @@ int lu_panel(feast_ctx* ctx, int64_t n, c128* Z, int64_t lda, int j0, int w, int
     void* args[] = {&a};
     CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void*)lu_panel_kernel, dim3(G), dim3(256), args, smem, ctx->stream));
     ctx->launches++;
-    if (n > w) {
-        laswp_kernel<<<ceil_div(n - w, 256), 256, 0, ctx->stream>>>(Z, lda, (int)n, ipiv, j0, j0 + w);
+    if (ncols > w) {   // ncols: columns of the (possibly rectangular) row-major window the interchanges apply to
+        laswp_kernel<<<ceil_div(ncols - w, 256), 256, 0, ctx->stream>>>(Z, lda, (int)ncols, ipiv, j0, j0 + w);
         KLAUNCH_CHECK(ctx);
     }
     return 0;
 }
 
-int lu_rec(feast_ctx* ctx, int64_t n, c128* Z, int64_t lda, int j0, int w, int* ipiv, LUWork& wk) {
-    if (w <= PW) return lu_panel(ctx, n, Z, lda, j0, w, ipiv, wk);
+int lu_rec(feast_ctx* ctx, int64_t n, c128* Z, int64_t lda, int j0, int w, int* ipiv, LUWork& wk, int64_t ncols) {
+    if (w <= PW) return lu_panel(ctx, n, Z, lda, j0, w, ipiv, wk, ncols);
     int h = ((w / 2 + 31) / 32) * 32;
     if (h >= w) h = w - 32;
     const int w2 = w - h;
-    FEAST_TRY(lu_rec(ctx, n, Z, lda, j0, h, ipiv, wk));
+    FEAST_TRY(lu_rec(ctx, n, Z, lda, j0, h, ipiv, wk, ncols));
     // right part (its rows were already interchanged panel by panel): U12 = L11^-1 A12, A22 -= L21 U12
     c128* A11 = Z + (int64_t)j0 * lda + j0;          // row-major blocks
     c128* A12 = A11 + h;
@@ -321,7 +321,7 @@ int lu_rec(feast_ctx* ctx, int64_t n, c128* Z, int64_t lda, int j0, int w, int* 
     FEAST_TRY((trsm_rec<true, true>(ctx, h, w2, A11, lda, 1, false, A12, lda, 1)));
     const int mrows = (int)(n - j0 - h);
     FEAST_TRY(launch_zgemm(ctx, mrows, w2, h, hc128(-1, 0), A21, lda, 1, false, A12, lda, 1, hc128(1, 0), A22, lda, 1));
-    FEAST_TRY(lu_rec(ctx, n, Z, lda, j0 + h, w2, ipiv, wk));
+    FEAST_TRY(lu_rec(ctx, n, Z, lda, j0 + h, w2, ipiv, wk, ncols));
     return 0;
 }
 
@@ -337,7 +337,7 @@ int dense_getrf(feast_ctx* ctx, int64_t n, c128* Z, int* ipiv_d, int* info_out) 
     wk.info = (int*)base;
     CUDA_TRY(ctx, cudaMemsetAsync(wk.info, 0, sizeof(int), ctx->stream));
     // NOTE: the split-K path of launch_zgemm also uses red_d; LU GEMMs have beta = 1 so never split.
-    FEAST_TRY(lu_rec(ctx, n, Z, n, 0, (int)n, ipiv_d, wk));
+    FEAST_TRY(lu_rec(ctx, n, Z, n, 0, (int)n, ipiv_d, wk, n));
     if (info_out) {
         int* h = (int*)ctx->pinned;
         CUDA_TRY(ctx, cudaMemcpyAsync(h, wk.info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -345,6 +345,33 @@ int dense_getrf(feast_ctx* ctx, int64_t n, c128* Z, int* ipiv_d, int* info_out) 
         *info_out = *h;
     }
     return 0;
+}
+
+// LU with partial pivoting of the first w columns of a ROW-major window of `rows` rows and `ncols` columns (lda >= ncols):
+// the row interchanges (ipiv, absolute rows of the window) are applied to all ncols columns, the elimination only to the
+// first w (the caller finishes the remaining columns with dense_trsm + launch_zgemm).  Used by the pivoted band LU.
+int dense_getrf_rect(feast_ctx* ctx, int rows, int w, int ncols, c128* Z, int64_t lda, int* ipiv_d, int* info_out) {
+    LUWork wk;
+    char* base = (char*)ctx->red_d;
+    wk.cand = (Cand*)base;                        base += sizeof(Cand) * 2 * kNumSMs;
+    wk.candrow = (c128*)base;                     base += sizeof(c128) * 2 * kNumSMs * PW;
+    wk.diagrow = (c128*)base;                     base += sizeof(c128) * 2 * PW;
+    wk.info = (int*)base;
+    CUDA_TRY(ctx, cudaMemsetAsync(wk.info, 0, sizeof(int), ctx->stream));
+    FEAST_TRY(lu_rec(ctx, rows, Z, lda, 0, w, ipiv_d, wk, ncols));
+    if (info_out) {
+        int* h = (int*)ctx->pinned;
+        CUDA_TRY(ctx, cudaMemcpyAsync(h, wk.info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        *info_out = *h;
+    }
+    return 0;
+}
+
+// B (h x ncols, row-major ldb) <- T^-1 B with the lower-unit or upper-non-unit triangle of a row-major T (ldt)
+int dense_trsm(feast_ctx* ctx, bool lower_unit, int h, int ncols, const c128* T, int64_t ldt, c128* B, int64_t ldb) {
+    if (lower_unit) return trsm_rec<true, true>(ctx, h, ncols, T, ldt, 1, false, B, ldb, 1);
+    return trsm_rec<false, false>(ctx, h, ncols, T, ldt, 1, false, B, ldb, 1);
 }
 
 int dense_build_perm(feast_ctx* ctx, int64_t n, const int* ipiv_d, int* perm_d) {

@@ -87,6 +87,10 @@ void band_free(BandFactor& F);
 int band_solve_refined(feast_ctx* ctx, const BandFactor& F, const c128* zvals, int m, const c128* Rhs, c128* Y, c128* work,
                        int* steps_out, double* relres_out);
 int dense_build_diag_inverses(feast_ctx* ctx, int64_t n, const c128* LU, c128* dinv);
+// pivoted LU of the first w columns of a rows x ncols row-major window (interchanges applied to all ncols columns)
+int dense_getrf_rect(feast_ctx* ctx, int rows, int w, int ncols, c128* Z, int64_t lda, int* ipiv_d, int* info_out);
+// B (h x ncols, row-major ldb) <- T^-1 B, T = lower-unit or upper-non-unit triangle of a row-major matrix (ldt)
+int dense_trsm(feast_ctx* ctx, bool lower_unit, int h, int ncols, const c128* T, int64_t ldt, c128* B, int64_t ldb);
 int dense_build_perm(feast_ctx* ctx, int64_t n, const int* ipiv_d, int* perm_d);
 size_t spmm_partials_bytes(int m);
 int debug_check_finite(feast_ctx* ctx, const void* p, int64_t ndoubles, const char* name);
