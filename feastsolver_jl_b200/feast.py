@@ -405,7 +405,8 @@ def gen_feast(X, A, B, contour: Contour | None = None, *, nodes=8, iter=10, c=co
 
 
 def nlfeast(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=10e-12, store=True,
-            spurious=1e-5, factorizer=None, left_divider=None, ctx=None, solver_opts=None, stats=None, comm=None):
+            spurious=1e-5, factorizer=None, left_divider=None, ctx=None, solver_opts=None, stats=None, comm=None,
+            _stop_rule="nlfeast"):
     """nlfeast!(T, X, nodes, iter; ...)  (src/nlfeast.jl:2-84) -> (L, X, res), all m0, unfiltered.
 
     ADDED METHOD: `T` is the list of polynomial coefficient matrices
@@ -433,13 +434,20 @@ def nlfeast(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=1
         ctx.set_contour(contour.nodes, contour.weights)
         if ctx.nranks > 1:
             ctx.set_node_owners(node_owners(contour.nodes, ctx.nranks))
-        ctx.set_solver(store=store, **(solver_opts or {}))
+        sched = getattr(solver_opts, "tol_schedule", None)    # (first pass, later passes): nlfeast_it
+        base_opts = dict(solver_opts or {})
+        if sched is not None:
+            base_opts["inner_tol"] = sched[0]
+        ctx.set_solver(store=store, **base_opts)
         ctx.set_subspace(X)
         ctx.orthonormalize_X()  # nlfeast.jl:12-13
         Lam = np.zeros(m0, complex)
         res = np.zeros(m0)
         hist = []
         for nit in range(iter + 1):
+            if sched is not None and nit == 1:
+                base_opts["inner_tol"] = sched[1]
+                ctx.set_solver(store=store, **base_opts)   # same solver kind: the device layout is kept
             st = ctx.contour_apply(Lam if nit > 0 else None, first_pass=(nit == 0))  # nlfeast.jl:36-61
             Rf, G1 = ctx.beyn_reduce()  # utils.jl:70-71 (tall part)
             U, S, Vh = sla.svd(Rf, check_finite=False)  # m0 x m0 (host)
@@ -457,6 +465,10 @@ def nlfeast(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=1
             hist.append(rec)
             if debug:
                 iter_debug_print(nit, Lam, res, CircularContour(c, r, contour.nodes, contour.weights), spurious)
+            if _stop_rule == "it":
+                if nit >= 1 and res_inside.size > 0 and res_inside.max() < eps:  # nlfeast.jl:164 (checked from the 2nd pass on)
+                    break
+                continue
             if res_inside.size > 0 and res_inside.max() < eps:  # nlfeast.jl:73
                 break
             good = res_inside[res_inside < spurious]
@@ -471,6 +483,51 @@ def nlfeast(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=1
         if own_ctx:
             ctx.close()
     return Lam, X, res
+
+
+def ifeast(A, X0, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=0.05, ctx=None, solver_opts=None, stats=None):
+    """ifeast!(A, X0, nodes, iter; c, r, debug, eps)  (src/feast_experimental.jl:1-60): FEAST with INEXACT inner solves,
+    exactly `iter` contour passes, all m0 Ritz pairs returned unfiltered with absolute residuals; X0 is not mutated.
+
+    The reference applies (zI - A)^-1 to X column by column with bicgstabl and solves the generalized reduced problem
+    (Q'AQ, Q'Q).  On the device the same filter is applied in residual-inverse-iteration form -- (zI - A)^-1 x_j =
+    (x_j - (A - zI)^-1 R_j) / (z - l_j) exactly -- by the pseudo-block Krylov solver over the tiled SpMM (one SpMM per
+    iteration for all m0 columns), and Q is orthonormalised before the projection (same Ritz pairs).  A must be sparse
+    (the Krylov path has no dense operator); the inner tolerance defaults to IterativeSolvers' sqrt(eps).
+    """
+    N, m0 = X0.shape
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("Incorrect dimensions of A, must be square")       # feast_experimental.jl:4
+    if A.shape[0] != N:
+        raise ValueError("Incorrect dimensions of X0, must match A")        # :6
+    if not sp.issparse(A):
+        raise TypeError("ifeast on the B200 path needs a sparse A (Krylov inner solves); use feast for dense operators")
+    opts = {"kind": _lib.SOLVER_KRYLOV, "inner_tol": float(np.sqrt(np.finfo(float).eps)), "max_inner": 4000}
+    opts.update(solver_opts or {})
+    X = np.array(X0, dtype=np.complex128, order="F")                        # X = deepcopy(X0), :9
+    st = {} if stats is None else stats
+    contour = circular_contour_trapezoidal(c, r, nodes)                     # theta of :15
+    _linear_driver(X, A, None, contour, iter, -1.0, debug, False, ctx, opts, False, st, None)   # eps < 0: never stops early
+    return st["Lam_all"], X, st["res_all"]
+
+
+def nlfeast_it(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=0.05, ctx=None, solver_opts=None,
+               stats=None):
+    """nlfeast_it!(T, X, nodes, iter; c, r, debug, eps)  (src/nlfeast.jl:87-171): nlfeast with inexact inner solves --
+    relative tolerance 1e-3 in the first contour pass (:106), 1e-8 afterwards (:139) -- stopping when
+    max(res[inside]) < eps (:164).  `T` is the list of polynomial coefficients (see nlfeast).  The warm start from the
+    previous solution (`Tinv`, nodes x N x m0 of storage upstream) is not kept on the device: in residual-inverse-
+    iteration form the right-hand side R shrinks with the outer iteration, which plays the same role.
+    """
+    class _Sched(dict):      # inner tolerance schedule read by nlfeast before every contour pass
+        pass
+    opts = _Sched({"kind": _lib.SOLVER_KRYLOV, "max_inner": 4000})
+    opts.update(solver_opts or {})
+    opts.tol_schedule = (1e-3, 1e-8)
+    st = {} if stats is None else stats
+    lam, X, res = nlfeast(T, X, nodes, iter, c=c, r=r, debug=debug, eps=eps, store=False, ctx=ctx, solver_opts=opts, stats=st,
+                          _stop_rule="it")
+    return lam, X, res
 
 
 def contour_estimate_eig(A, contour, B=I, *, samples=None, eps=1e-12, debug=False, mixed_prec=False,

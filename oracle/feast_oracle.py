@@ -505,6 +505,94 @@ def nlfeast(T, X, nodes, iter, *, c=0.0 + 0.0j, r=1.0, eps=10e-12, store=True,
     return Lam, X, res
 
 
+# --------------------------------------------------------------------------
+# inexact-inner-solve precedents  (src/feast_experimental.jl:1-60, src/nlfeast.jl:87-171)
+# --------------------------------------------------------------------------
+
+def _bicgstab_cols(Z, Bm, tol, X0=None, maxiter=None):
+    """Column-by-column Krylov solves as in `for m=1:m0 temp[:, m] .= bicgstabl(ZmA, X[:, m])`
+    (feast_experimental.jl:27-29).  IterativeSolvers.bicgstabl is restated with scipy's BiCGStab
+    (same Krylov family; only the achieved tolerance matters to the outer iteration)."""
+    import scipy.sparse.linalg as spla
+    Bm = np.asarray(Bm, dtype=complex)
+    out = np.zeros_like(Bm)
+    for j in range(Bm.shape[1]):
+        x0 = None if X0 is None else np.ascontiguousarray(X0[:, j])
+        x, info = spla.bicgstab(Z, Bm[:, j], x0=x0, rtol=tol, atol=0.0, maxiter=maxiter)
+        out[:, j] = x
+    return out
+
+
+def ifeast(A, X0, nodes, iter, *, c=0.0 + 0.0j, r=1.0, eps=0.05, tol=None):
+    """ifeast!(A, X0, nodes, iter; c, r, debug, eps)  (src/feast_experimental.jl:1-60): plain (non-RII) FEAST with
+    inexact per-column Krylov solves of (zI - A) Y = X, `iter` passes, NO orthonormalisation (the reduced problem is
+    generalized: Aq = Q'AQ, Bq = Q'Q), returns ALL m0 Ritz pairs with absolute residuals ||A x - x l||."""
+    N, m0 = X0.shape
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("Incorrect dimensions of A, must be square")
+    if A.shape[0] != N:
+        raise ValueError("Incorrect dimensions of X0, must match A")
+    tol = np.sqrt(np.finfo(float).eps) if tol is None else tol   # IterativeSolvers' default reltol
+    X = np.array(X0, dtype=complex)
+    theta = np.linspace(np.pi / nodes, 2 * np.pi - np.pi / nodes, nodes)
+    Lam = np.zeros(m0, complex)
+    res = np.zeros(m0)
+    eye = sp.identity(N, format="csr", dtype=complex) if _is_sparse(A) else np.eye(N, dtype=complex)
+    for _ in range(iter):
+        Q = np.zeros((N, m0), complex)
+        for i in range(nodes):
+            z = r * np.exp(1j * theta[i]) + c
+            ZmA = eye * z - A
+            Q += _bicgstab_cols(ZmA, X, tol) * (np.exp(1j * theta[i]) / nodes)     # :31 (no factor r upstream)
+        Aq = Q.conj().T @ (A @ Q)
+        Bq = Q.conj().T @ Q
+        w, v = sla.eig(Aq, Bq, check_finite=False)
+        Lam, v = _julia_eig_sort(w, v)
+        X = Q @ v
+        X = X / np.linalg.norm(X, axis=0)[None, :]
+        res = np.linalg.norm(A @ X - X * Lam[None, :], axis=0)
+    return Lam, X, res
+
+
+def nlfeast_it(T, X, nodes, iter, *, c=0.0 + 0.0j, r=1.0, eps=0.05):
+    """nlfeast_it!(T, X, nodes, iter; c, r, debug, eps)  (src/nlfeast.jl:87-171): nlfeast with per-column bicgstabl
+    solves, tolerance 1e-3 in the first pass (:106) and 1e-8 warm-started from the previous solution afterwards
+    (:139); stops when max(res[inside]) < eps (:164); returns all m0 pairs, relative residuals."""
+    N, m0 = X.shape
+    theta = np.linspace(np.pi / nodes, 2 * np.pi - np.pi / nodes, nodes)
+    zs = r * np.exp(1j * theta) + c
+    ws = r * np.exp(1j * theta) / nodes
+    Tz = [T(z) for z in zs]
+    Tinv = [None] * nodes
+    Q0 = np.zeros((N, m0), complex)
+    Q1 = np.zeros((N, m0), complex)
+    for i in range(nodes):
+        Tinv[i] = _bicgstab_cols(Tz[i], X, 1e-3)
+        Q0 += Tinv[i] * ws[i]
+        Q1 += Tinv[i] * ws[i] * zs[i]
+    Lam, Xn = beyn_svd_step(Q0, Q1)
+    X[:, :] = Xn
+    R = update_R_nep(X, Lam, T)
+    res = residuals_nep(R, Lam, T)
+    for nit in range(1, iter + 1):
+        Q0[:] = 0
+        Q1[:] = 0
+        for i in range(nodes):
+            Tinv[i] = _bicgstab_cols(Tz[i], R, 1e-8, X0=Tinv[i])
+            Tm = (X - Tinv[i]) * (ws[i] / (zs[i] - Lam))[None, :]
+            Q0 += Tm
+            Q1 += Tm * zs[i]
+        Lam, Xn = beyn_svd_step(Q0, Q1)
+        X[:, :] = Xn
+        R = update_R_nep(X, Lam, T)
+        res = residuals_nep(R, Lam, T)
+        inside = np.abs(Lam - c) <= r
+        if inside.any() and res[inside].max() < eps:
+            break
+    X[:, :] = normalize_cols(X)
+    return Lam, X, residuals_nep(update_R_nep(X, Lam, T), Lam, T)
+
+
 def polynomial(coeffs):
     """T(z) = sum_i z^i A_i, the closures of test/butterfly.jl:61, test/polynomial.jl:9-11."""
     def T(z):

@@ -557,3 +557,46 @@ def test_empty_contour_returns_empty(fs, capsys):
     e, v, r = fs.feast(x0(10, 3, 0), A, nodes=8, iter=2, c=100.0, r=0.5)
     assert e.size == 0 and v.shape == (10, 0) and r.size == 0
     assert "no eigenvalues found in contour!" in capsys.readouterr().out  # feast.jl:78
+
+
+# ----------------------------------------------------------------------------- inexact-inner-solve drivers
+# Written after the round's GPU budget was spent: they compose validated pieces (linear / polynomial drivers with Krylov
+# inner solves) but have not run on a GPU yet, hence gated.  FEAST_RUN_EXPERIMENTAL=1 runs them.
+_experimental = pytest.mark.skipif(not os.environ.get("FEAST_RUN_EXPERIMENTAL"), reason="not yet validated on a GPU")
+
+
+@_experimental
+def test_ifeast_matches_oracle(fs):
+    """ifeast! (src/feast_experimental.jl:1-60): all m0 Ritz pairs after `iter` passes with inexact solves."""
+    n, m0 = 2000, 12
+    A = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(n, n), format="csc")
+    exact = 2.0 - 2.0 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
+    c = r = 0.5 * (exact[7] + exact[8]) / 2.0
+    X0 = x0(n, m0, 4)
+    lam, X, res = fs.ifeast(A, X0, 16, 4, c=c, r=r)
+    assert lam.shape == (m0,) and X.shape == (n, m0) and res.shape == (m0,)
+    inside = np.abs(lam - c) <= r
+    want = exact[np.abs(exact - c) <= r]
+    assert inside.sum() == want.size
+    match_eigs(lam[inside], want)
+    assert res[inside].max() < 1e-9
+    assert np.allclose(np.linalg.norm(X, axis=0), 1.0)
+    with pytest.raises(TypeError):
+        fs.ifeast(A.toarray(), X0, 8, 1)
+
+
+@_experimental
+def test_nlfeast_it_linear_pencil(fs):
+    """nlfeast_it! (src/nlfeast.jl:87-171) on T(z) = zI - A with Krylov inner solves (1e-3, then 1e-8)."""
+    n, m0 = 2000, 10
+    A = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(n, n), format="csc")
+    exact = 2.0 - 2.0 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))
+    c = r = 0.5 * (exact[5] + exact[6]) / 2.0
+    coeffs = [-A, sp.identity(n, format="csc")]
+    X0 = x0(n, m0, 6)
+    lam, X, res = fs.nlfeast_it(coeffs, X0.copy(), 16, 8, c=c, r=r, eps=1e-9)
+    inside = np.abs(lam - c) <= r
+    want = exact[np.abs(exact - c) <= r]
+    assert inside.sum() == want.size
+    match_eigs(lam[inside], want)
+    assert res[inside].max() < 1e-9
