@@ -13,7 +13,7 @@ module FEASTSolverB200
 using LinearAlgebra
 using SparseArrays
 
-export feast!, gen_feast!, dual_gen_feast!, nlfeast!, contour_estimate_eig
+export feast!, gen_feast!, dual_gen_feast!, nlfeast!, ifeast!, contour_estimate_eig
 export in_contour, circular_contour_trapezoidal, circular_contour_gauss,
        rectangular_contour_gauss, rectangular_contour_trapezoidal, rational_func
 export Contour, CircularContour, RectangularContour, CustomContour
@@ -119,7 +119,7 @@ function _check_plugins(factorizer, left_divider, mixed_prec)
 end
 
 # ---------------------------------------------------------------- linear drivers
-function _linear!(X, A, B, contour, iter, ϵ, debug, store, generalized)
+function _linear!(X, A, B, contour, iter, ϵ, debug, store, generalized; solver_kind=0, inner_tol=1e-8, unfiltered=false)
     N, m₀ = size(X)
     size(A, 1) != size(A, 2) && error("Incorrect dimensions of A, must be square")   # feast.jl:13
     size(A, 1) != N && error("Incorrect dimensions of X, must match A")                 # feast.jl:15
@@ -132,7 +132,7 @@ function _linear!(X, A, B, contour, iter, ϵ, debug, store, generalized)
     _ck(ctx, ccall((:feast_set_problem, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint), ctx.h, generalized ? 1 : 0, generalized ? 2 : 1))
     z = convert(Vector{ComplexF64}, contour.nodes); w = convert(Vector{ComplexF64}, contour.weights)
     _ck(ctx, ccall((:feast_set_contour, libfeast), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}), ctx.h, length(z), z, w))
-    _ck(ctx, ccall((:feast_set_solver, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cint, Cint), ctx.h, 0, 0, 1e-8, 4000, store))
+    _ck(ctx, ccall((:feast_set_solver, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cint, Cint), ctx.h, solver_kind, 0, inner_tol, 4000, store))
     Xc = convert(Matrix{ComplexF64}, X)
     _ck(ctx, ccall((:feast_set_subspace, libfeast), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{ComplexF64}, Int64), ctx.h, N, m₀, Xc, N))
     Λ, res = zeros(ComplexF64, m₀), zeros(m₀)
@@ -158,6 +158,7 @@ function _linear!(X, A, B, contour, iter, ϵ, debug, store, generalized)
     _ck(ctx, ccall((:feast_get_X, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Int64), ctx.h, Xc, N))
     X .= Xc
     finalize(ctx)
+    unfiltered && return Λ, X, res
     inside = in_contour(Λ, contour)
     !reduce(|, inside) && println("no eigenvalues found in contour!")
     Λ[inside], X[:, inside], res[inside]
@@ -251,6 +252,16 @@ function contour_estimate_eig(A::AbstractMatrix, contour::Contour, B=I; samples:
     _ck(ctx, ccall((:feast_estimate_count, libfeast), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ptr{Cvoid}), ctx.h, est, C_NULL); allow=(0, 2000))
     finalize(ctx)
     est[]
+end
+
+# ifeast!(A, X0, nodes, iter; c, r, debug, ϵ)  (src/feast_experimental.jl:1-60): inexact inner solves, exactly `iter`
+# passes, all m0 pairs returned; on the device the filter is applied in residual-inverse-iteration form by the Krylov path.
+function ifeast!(A::AbstractMatrix, X₀::AbstractMatrix, nodes::Integer, iter::Integer;
+                 c=complex(0.0, 0.0), r=1.0, debug=false, ϵ=0.05)
+    issparse(A) || error("ifeast! on the B200 path needs a sparse A (Krylov inner solves)")
+    X = convert(Matrix{ComplexF64}, deepcopy(X₀))
+    _linear!(X, A, I, circular_contour_trapezoidal(c, r, nodes), iter, -1.0, debug, false, false;
+             solver_kind=2, inner_tol=sqrt(eps(Float64)), unfiltered=true)
 end
 
 # ---------------------------------------------------------------- nonlinear driver (added method: coefficients)
