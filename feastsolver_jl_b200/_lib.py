@@ -90,6 +90,7 @@ SIGNATURES = {
     "feast_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),
     "feast_launch_count": (_i64, [_vp]),
     "feast_phase_times": (_i, [_vp, _vp, _i]),
+    "feast_set_mixed_precision": (_i, [_vp, _i]),
     "feast_layout_info": (_i, [_vp, _vp, C.POINTER(C.c_double)]),
     "feast_debug_cholqr": (_i, [_i64, _i, _vp, _i64, _vp, C.POINTER(_i)]),
     "feast_debug_tile_plan": (_i, [_i64, _vp, _vp, _i, _i, _i, _i, _i, _vp, C.POINTER(_i), C.POINTER(C.c_double)]),

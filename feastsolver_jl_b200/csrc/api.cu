@@ -550,6 +550,13 @@ int apply_slot_adjoint(feast_ctx* ctx, int slot, const c128* V, c128* W) {
     return feast_fail(ctx, FEAST_ERR_STATE, "operator slot %d is not set", slot);
 }
 
+// Krylov inner solve; COCG with complex64 block storage when mixed precision was requested and is applicable
+int krylov_any(feast_ctx* ctx, int method, const c128* zvals, const c128* rhs, c128* Y, KrylovResult* kr) {
+    if (ctx->mixed_prec && method == FEAST_KRYLOV_COCG && (ctx->m0 % 2) == 0 && ctx->m0 <= 128 && ctx->tiles_ok && ctx->tile_cfg == 0)
+        return krylov_solve_mixed(ctx, zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, kr);
+    return krylov_solve(ctx, method, zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, kr);
+}
+
 // One shifted solve  (sum_i coef[i] slot_i) Y = rhs  with m0 right-hand sides: dense LU (stored per node
 // when store != 0, node index k >= 0) or Krylov on the union pattern.  `e1` is recorded between the
 // factorisation/assembly and the solve.  This is linsolve! (src/utils.jl:175-179) for one contour node.
@@ -614,10 +621,10 @@ int solve_shifted(feast_ctx* ctx, int solver, int method, int k, const hc128* co
                 return feast_fail(ctx, FEAST_ERR_STATE, "adjoint Krylov solve needs symmetric operators: pass them dense");
             FEAST_TRY(ensure_block(ctx, ctx->W2));
             FEAST_TRY(launch_conj(ctx, n * m, rhs, ctx->W2.p));
-            FEAST_TRY(krylov_solve(ctx, method, ctx->zvals, ctx->W2.p, Y, ctx->inner_tol, ctx->max_inner, &kr));
+            FEAST_TRY(krylov_any(ctx, method, ctx->zvals, ctx->W2.p, Y, &kr));
             FEAST_TRY(launch_conj(ctx, n * m, Y, Y));
         } else {
-            FEAST_TRY(krylov_solve(ctx, method, ctx->zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, &kr));
+            FEAST_TRY(krylov_any(ctx, method, ctx->zvals, rhs, Y, &kr));
         }
         st.inner_iters_total += kr.iters;
         st.inner_iters_max = std::max(st.inner_iters_max, kr.iters);
@@ -827,6 +834,12 @@ int feast_set_solver(feast_ctx* ctx, int kind, int krylov, double inner_tol, int
         FEAST_TRY(build_union(ctx));
         ctx->problem_ready = true;
     }
+    return 0;
+}
+
+int feast_set_mixed_precision(feast_ctx* ctx, int on) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ctx->mixed_prec = on ? 1 : 0;
     return 0;
 }
 

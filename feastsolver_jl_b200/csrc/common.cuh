@@ -152,6 +152,7 @@ struct feast_ctx {
     double inner_tol = 1e-10;
     int max_inner = 5000;
     int store = 0;
+    int mixed_prec = 0;           // EXPERIMENTAL: complex64 storage of the COCG blocks (feast_set_mixed_precision)
     std::vector<DenseLU> stored;  // per node (only local nodes populated)
     std::vector<BandFactor> bstored; // per node, banded solver
     BandFactor bscratch;          // store=0

@@ -10,6 +10,8 @@
 int launch_spmm(feast_ctx* ctx, int64_t n, int m, const int* rowptr, const int* col,
                 const double* rvals, const c128* cvals, const c128* X, int ldx, c128* Y, int ldy,
                 c128* dot_out);
+// EXPERIMENTAL mixed-precision variant: blocks stored as complex64 (n x m0, m0 even), products accumulated in double
+int launch_spmm_f32(feast_ctx* ctx, int m0, const c128* zvals, const void* X32, void* Y32, c128* dot_out);
 // zvals[e] = sum_i coef[i] * slotvals_i[e]   (K1 / K9: shifted / polynomial assembly)
 int launch_assemble_union(feast_ctx* ctx, int64_t unnz, int nslots, const double* const* rv,
                           const c128* const* cv, const hc128* coef, c128* zvals);
@@ -67,6 +69,8 @@ struct KrylovResult { int iters; double relres_max; bool converged; double spmm_
 int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs, c128* Y,
                  double tol, int maxit, KrylovResult* out);
 
+// EXPERIMENTAL: COCG with complex64 storage of the Krylov blocks (mixed_prec); needs m0 even and the default tile plan
+int krylov_solve_mixed(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out);
 int gmres_solve(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out);
 size_t gmres_small_bytes(int m, int R);
 

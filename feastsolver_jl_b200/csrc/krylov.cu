@@ -407,6 +407,144 @@ int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs,
     return 0;
 }
 
+// =============================================================================== mixed-precision COCG (EXPERIMENTAL)
+// The reference's `mixed_prec=true` (src/feast.jl:19-25: ComplexF32 factorisation and solve inside the double-precision
+// RII loop) on the Krylov path: the four COCG blocks (x, r, p, q) are STORED in complex64, which halves the HBM traffic
+// of every kernel of the iteration; all arithmetic (products, axpys, dots, the per-column recurrences) is done in double
+// on the loaded values.  The attainable inner residual is limited by the complex64 rounding of r (~1e-6 relative), the
+// outer RII loop corrects in double.  NOT YET RUN ON A GPU (written after the round's GPU budget was spent).
+namespace {
+
+typedef float2 c64;
+__device__ __forceinline__ c128 up(c64 v) { return cmake((double)v.x, (double)v.y); }
+__device__ __forceinline__ c64 down(c128 v) { return make_float2((float)v.x, (float)v.y); }
+
+// r = p = (complex64) b ; x = 0
+__global__ void cocg32_init_kernel(int64_t total, const c128* __restrict__ b, c64* __restrict__ r, c64* __restrict__ p,
+                                   c64* __restrict__ x) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const c64 v = down(b[t]);
+        r[t] = v; p[t] = v; x[t] = make_float2(0.f, 0.f);
+    }
+}
+// r -= alpha q ; partials of <r,r> (unconjugated) and ||r||^2 -- same layout as cocg_update_kernel
+__global__ void __launch_bounds__(256)
+cocg32_update_kernel(int64_t n, int m, c64* __restrict__ r, const c64* __restrict__ q, KryScal s, double* __restrict__ partials) {
+    extern __shared__ double sm[];  // [256][3]
+    int cw = 1;
+    while (cw < m && cw < 256) cw <<= 1;
+    const int rpp = 256 / cw, cj = threadIdx.x % cw, rr = threadIdx.x / cw;
+    for (int jbase = 0; jbase < m; jbase += cw) {
+        const int j = jbase + cj;
+        double re = 0.0, im = 0.0, nn = 0.0;
+        if (j < m) {
+            const c128 a = s.alpha[j];
+            const c128 na = cmake(-a.x, -a.y);
+            const bool act = s.active[j] != 0;
+            for (int64_t i = (int64_t)blockIdx.x * rpp + rr; i < n; i += (int64_t)gridDim.x * rpp) {
+                const int64_t t = i * m + j;
+                c128 rv = up(r[t]);
+                if (act) {
+                    cfma(rv, na, up(q[t]));
+                    const c64 st = down(rv);
+                    r[t] = st;
+                    rv = up(st);      // the recurrence continues from the STORED value
+                }
+                re = fma(rv.x, rv.x, re); re = fma(-rv.y, rv.y, re);
+                im = fma(2.0 * rv.x, rv.y, im);
+                nn = fma(rv.x, rv.x, nn); nn = fma(rv.y, rv.y, nn);
+            }
+        }
+        sm[3 * threadIdx.x] = re; sm[3 * threadIdx.x + 1] = im; sm[3 * threadIdx.x + 2] = nn;
+        __syncthreads();
+        if (rr == 0 && j < m) {
+            for (int k = 1; k < rpp; ++k) {
+                re += sm[3 * (k * cw + cj)]; im += sm[3 * (k * cw + cj) + 1]; nn += sm[3 * (k * cw + cj) + 2];
+            }
+            double* o = partials + (int64_t)blockIdx.x * 3 * m + 3 * j;
+            o[0] = re; o[1] = im; o[2] = nn;
+        }
+        __syncthreads();
+    }
+}
+// x += alpha p ; p = r + beta p
+__global__ void cocg32_p_kernel(int64_t total, int m, c64* __restrict__ x, c64* __restrict__ p, const c64* __restrict__ r, KryScal s) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(t % m);
+        const c128 a = s.alpha[j];
+        if (a.x == 0.0 && a.y == 0.0) continue;
+        const c128 pv = up(p[t]);
+        c128 xv = up(x[t]);
+        cfma(xv, a, pv);
+        x[t] = down(xv);
+        if (s.active[j]) {
+            c128 v = up(r[t]);
+            cfma(v, s.beta[j], pv);
+            p[t] = down(v);
+        }
+    }
+}
+__global__ void c64_to_c128_kernel(int64_t total, const c64* __restrict__ src, c128* __restrict__ dst) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) dst[t] = up(src[t]);
+}
+
+}  // namespace
+
+int krylov_solve_mixed(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out) {
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    const int64_t total = n * m;
+    KryScal s = carve_scalars(ctx);
+    const double tol2 = tol * tol;
+    // four complex64 blocks inside the three complex128 Krylov work blocks
+    c64* r = (c64*)ctx->kr.p;
+    c64* x = r + total;
+    c64* p = (c64*)ctx->kp.p;
+    c64* q = (c64*)ctx->kq.p;
+    cudaStream_t st = ctx->stream;
+    struct HostFlag { int nactive; int pad; double relmax; };
+    HostFlag* hf = (HostFlag*)ctx->pinned;
+    const int check_every = 8;
+    cocg32_init_kernel<<<ew_grid_k(total), 256, 0, st>>>(total, Rhs, r, p, x);
+    KLAUNCH_CHECK(ctx);
+    FEAST_TRY(launch_colnorm2(ctx, n, m, Rhs, s.bn2));
+    FEAST_TRY(launch_coldot(ctx, n, m, Rhs, Rhs, false, s.rho));
+    kry_init_scalars<<<1, 128, 0, st>>>(m, s, tol2);
+    KLAUNCH_CHECK(ctx);
+    const int rgrid = red_grid_k(n, m);
+    hf->nactive = -1;
+    hf->relmax = 1.0;
+    int iters = 0;
+    while (iters < maxit) {
+        FEAST_TRY(launch_spmm_f32(ctx, m, zvals, p, q, s.mu));        // q = Z p, mu = <p, q>
+        cocg_alpha_kernel<<<1, 128, 0, st>>>(m, s);
+        KLAUNCH_CHECK(ctx);
+        cocg32_update_kernel<<<rgrid, 256, 768 * sizeof(double), st>>>(n, m, r, q, s, ctx->red_d);
+        KLAUNCH_CHECK(ctx);
+        cocg_beta_kernel<<<1, 1024, 3 * m * sizeof(double), st>>>(m, rgrid, ctx->red_d, s, tol2);
+        KLAUNCH_CHECK(ctx);
+        cocg32_p_kernel<<<ew_grid_k(total), 256, 0, st>>>(total, m, x, p, r, s);
+        KLAUNCH_CHECK(ctx);
+        ++iters;
+        if (iters % check_every == 0 || iters == maxit) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(&hf->nactive, s.nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaMemcpyAsync(&hf->relmax, s.relmax, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            if (hf->nactive == 0) break;
+        }
+    }
+    c64_to_c128_kernel<<<ew_grid_k(total), 256, 0, st>>>(total, x, Y);
+    KLAUNCH_CHECK(ctx);
+    if (out) {
+        out->iters = iters;
+        out->relres_max = hf->relmax;
+        out->converged = (hf->relmax <= tol * (1.0 + 1e-12));
+        out->spmm_ms = 0.0;
+        out->spmm_launches = 0;
+    }
+    return 0;
+}
+
 // =============================================================================== GMRES(R)
 // Pseudo-block restarted GMRES for general (non-symmetric) shifted operators: the m0 columns
 // share the SpMM and advance their own Arnoldi recurrences in lock step (per-column Hessenberg,

@@ -362,6 +362,126 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
     }
 }
 
+// ------------------------------------------------------------------ mixed-precision variant (EXPERIMENTAL)
+// Same tiled kernel for blocks stored in complex64 (the reference's `mixed_prec=true`: ComplexF32 solves inside the
+// double-precision RII loop, src/feast.jl:19-25).  A 16-byte unit of a row holds TWO complex64 columns, so the copy
+// geometry is the one of the complex128 kernel with half as many units per row (m0 = 64 -> one slab of 32 units, one
+// pass per tile); products and the fused <p, Zp> accumulate in double, the operator values stay complex128.
+// NOT YET RUN ON A GPU (written after the round's GPU budget was spent): reachable only through feast_set_mixed_precision.
+template <bool DOT, typename CFG>
+__global__ void __launch_bounds__(CFG::kThreads, CFG::kCtas)
+spmm_tiled_f32_kernel(int mu, int ntiles, const int* __restrict__ t_ptr, const int* __restrict__ t_hptr,
+                      const int* __restrict__ t_hidx, const int* __restrict__ rowptr, const uint16_t* __restrict__ lcol,
+                      const c128* __restrict__ val, const float4* __restrict__ X, int ldx, float4* __restrict__ Y, int ldy,
+                      double* __restrict__ partials) {
+    constexpr int G = 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t mbar;
+    float4* xs = (float4*)smem_raw;                                                    // [kRowsCap][SW] 16-byte units
+    c128* vs = (c128*)(smem_raw + TiledSmem<c128, CFG>::xs_bytes(G));                  // [kNnzCap]
+    uint16_t* ls = (uint16_t*)((unsigned char*)vs + TiledSmem<c128, CFG>::vs_bytes);   // [kNnzCap]
+    int* rs = (int*)((unsigned char*)ls + TiledSmem<c128, CFG>::ls_bytes);             // [kTileMax + 1]
+    constexpr int kTiledThreads = CFG::kThreads;
+    constexpr int NW = kTiledThreads / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane;
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t phase = 0;
+    c128 dacc[2][2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) { dacc[s][0] = cmake(0.0, 0.0); dacc[s][1] = cmake(0.0, 0.0); }
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int r0 = __ldg(t_ptr + tile), rows = __ldg(t_ptr + tile + 1) - r0;
+        const int hp = __ldg(t_hptr + tile);
+        const int nref = rows + __ldg(t_hptr + tile + 1) - hp;
+        const int ea = __ldg(rowptr + r0), eb = __ldg(rowptr + r0 + rows);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int j0 = s * G;
+            if (j0 >= mu) break;
+            const int SW = (mu - j0) < G ? (mu - j0) : G;
+            const uint32_t rowbytes = (uint32_t)SW * 16u;
+            if (tid == 0) {
+                uint32_t bytes = (uint32_t)nref * rowbytes;
+                if (s == 0) bytes += (uint32_t)(eb - ea) * (uint32_t)(sizeof(c128) + sizeof(uint16_t));
+                mbar_expect_tx(&mbar, bytes);
+            }
+            __syncthreads();
+            for (int t = lane * NW + warp; t < nref; t += kTiledThreads) {
+                const int srow = t < rows ? r0 + t : __ldg(t_hidx + hp + (t - rows));
+                bulk_g2s(xs + (size_t)t * SW, X + (int64_t)srow * ldx + j0, rowbytes, &mbar);
+            }
+            if (s == 0) {
+                if (eb > ea) {
+                    if (tid == 32) bulk_g2s(vs, val + ea, (uint32_t)(eb - ea) * (uint32_t)sizeof(c128), &mbar);
+                    if (tid == 64) bulk_g2s(ls, lcol + ea, (uint32_t)(eb - ea) * (uint32_t)sizeof(uint16_t), &mbar);
+                }
+                for (int t = tid; t <= rows; t += kTiledThreads) rs[t] = __ldg(rowptr + r0 + t) - ea;
+                __syncthreads();
+            }
+            mbar_wait(&mbar, phase);
+            phase ^= 1u;
+
+            const int gg = g < SW ? g : 0;
+            for (int lr = warp; lr < rows; lr += NW) {
+                const int e0 = rs[lr], e1 = rs[lr + 1];
+                c128 acc0 = cmake(0.0, 0.0), acc1 = cmake(0.0, 0.0);
+                for (int e = e0; e < e1; e += 8) {
+                    const uint4 iv = *reinterpret_cast<const uint4*>(ls + e);
+                    const unsigned w[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        unsigned lc[4];
+                        lc[0] = w[2 * h] & 0xFFFFu; lc[1] = w[2 * h] >> 16; lc[2] = w[2 * h + 1] & 0xFFFFu; lc[3] = w[2 * h + 1] >> 16;
+                        if (lc[0] == 0xFFFFu) break;
+                        float4 xv[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) xv[q] = xs[(size_t)(lc[q] == 0xFFFFu ? (unsigned)lr : lc[q]) * SW + gg];
+                        c128 vv[4];
+                        load_vals4(vs + e + 4 * h, vv);   // padding values are 0
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            cfma(acc0, vv[q], cmake((double)xv[q].x, (double)xv[q].y));
+                            cfma(acc1, vv[q], cmake((double)xv[q].z, (double)xv[q].w));
+                        }
+                    }
+                }
+                if (g < SW) {
+                    Y[(int64_t)(r0 + lr) * ldy + j0 + g] = make_float4((float)acc0.x, (float)acc0.y, (float)acc1.x, (float)acc1.y);
+                    if (DOT) {
+                        const float4 own = xs[(size_t)lr * SW + g];
+                        cfma(dacc[s][0], cmake((double)own.x, (double)own.y), acc0);
+                        cfma(dacc[s][1], cmake((double)own.z, (double)own.w), acc1);
+                    }
+                }
+            }
+        }
+    }
+    if (DOT) {
+        __syncthreads();
+        double* sred = (double*)smem_raw;   // [NW][2 slabs][G][4]
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            double* o = sred + (((size_t)warp * 2 + s) * G + g) * 4;
+            o[0] = dacc[s][0].x; o[1] = dacc[s][0].y; o[2] = dacc[s][1].x; o[3] = dacc[s][1].y;
+        }
+        __syncthreads();
+        // output t = 2 * column + (0: re, 1: im); column c lives in unit c / 2 = s * G + gq, half c & 1
+        for (int t = tid; t < 4 * mu; t += kTiledThreads) {
+            const int c = t >> 1, unit = c >> 1, s = unit / G, gq = unit - s * G;
+            const int comp = 2 * (c & 1) + (t & 1);
+            double acc = 0.0;
+            for (int wq = 0; wq < NW; ++wq) acc += sred[(((size_t)wq * 2 + s) * G + gq) * 4 + comp];
+            partials[(int64_t)blockIdx.x * 4 * mu + t] = acc;
+        }
+    }
+}
+
 template <typename VT, int G, typename CFG>
 int spmm_tiled_launch(feast_ctx* ctx, int m, const VT* val, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
     const size_t smem = TiledSmem<VT, CFG>::total(G) < 16384 ? 16384 : TiledSmem<VT, CFG>::total(G);
@@ -454,6 +574,42 @@ int launch_spmm(feast_ctx* ctx, int64_t n, int m, const int* rowptr, const int* 
             rc = rvals ? spmm_dispatch<double>(ctx, (int)n, mc, rowptr, col, rvals, X + j0, ldx, Y + j0, ldy, dchunk)
                        : spmm_dispatch<c128>(ctx, (int)n, mc, rowptr, col, cvals, X + j0, ldx, Y + j0, ldy, dchunk);
         if (rc) return rc;
+    }
+    return 0;
+}
+
+// q (n x m0 complex64) = Z p with the tiled kernel; dot_out (m0 complex128, optional) = sum_i p_ij q_ij.
+// Requires the default tile configuration, an even m0 <= 128 and a usable tile plan; returns FEAST_ERR_STATE otherwise.
+int launch_spmm_f32(feast_ctx* ctx, int m0, const c128* zvals, const void* X32, void* Y32, c128* dot_out) {
+    if (!ctx->tiles_ok || ctx->tile_cfg != 0 || (m0 & 1) || m0 > 128)
+        return feast_fail(ctx, FEAST_ERR_STATE, "mixed-precision SpMM needs the default tile plan and an even m0 <= 128");
+    typedef TileCfg0 CFG;
+    const int mu = m0 / 2;
+    const size_t smem = TiledSmem<c128, CFG>::total(32) < 32768 ? 32768 : TiledSmem<c128, CFG>::total(32);
+    const int ntiles = ctx->ntiles;
+    const int grid = ntiles < CFG::kCtas * kNumSMs ? ntiles : CFG::kCtas * kNumSMs;
+    static bool attr_done_dot[64] = {}, attr_done[64] = {};
+    const int dev = ctx->device & 63;
+    if (dot_out) {
+        auto kern = spmm_tiled_f32_kernel<true, CFG>;
+        if (!attr_done_dot[dev]) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kBudget));
+            attr_done_dot[dev] = true;
+        }
+        kern<<<grid, CFG::kThreads, smem, ctx->stream>>>(mu, ntiles, ctx->t_ptr, ctx->t_hptr, ctx->t_hidx, ctx->u_rowptr, ctx->u_lcol,
+                                                          zvals, (const float4*)X32, mu, (float4*)Y32, mu, ctx->red_d);
+        KLAUNCH_CHECK(ctx);
+        reduce_partials_kernel<<<ceil_div(2 * m0 * 32, 128), 128, 0, ctx->stream>>>(ctx->red_d, grid, 2 * m0, (double*)dot_out);
+        KLAUNCH_CHECK(ctx);
+    } else {
+        auto kern = spmm_tiled_f32_kernel<false, CFG>;
+        if (!attr_done[dev]) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kBudget));
+            attr_done[dev] = true;
+        }
+        kern<<<grid, CFG::kThreads, smem, ctx->stream>>>(mu, ntiles, ctx->t_ptr, ctx->t_hptr, ctx->t_hidx, ctx->u_rowptr, ctx->u_lcol,
+                                                          zvals, (const float4*)X32, mu, (float4*)Y32, mu, nullptr);
+        KLAUNCH_CHECK(ctx);
     }
     return 0;
 }

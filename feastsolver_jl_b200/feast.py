@@ -117,6 +117,9 @@ class FeastContext:
         return {"reordered": bool(info[0]), "ntiles": int(info[1]), "bandwidth": int(info[2]), "tiled_spmm": bool(info[3]),
                 "halo_rows_per_row": halo.value}
 
+    def set_mixed_precision(self, on=True):
+        self._ck(self.lib.feast_set_mixed_precision(self.h, int(bool(on))))
+
     def set_node_owners(self, owners):
         o = np.ascontiguousarray(owners, dtype=np.int32)
         self._ck(self.lib.feast_set_node_owners(self.h, len(o), _lib.ptr(o)))
@@ -286,12 +289,13 @@ def _default_device():
     return int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def _check_plugins(factorizer, left_divider, mixed_prec):
+def _check_plugins(factorizer, left_divider, mixed_prec, solver_opts=None):
     if factorizer is not None or left_divider is not None:
         raise FeastError(-1, "custom factorizer/left_divider callbacks cannot run inside libfeast_cuda "
                              "(no CPU fallback); use set_solver options instead")
-    if mixed_prec:
-        raise FeastError(-1, "mixed_prec=true is not implemented in this build (SURVEY 8f rank 2)")
+    if mixed_prec and (solver_opts or {}).get("kind") != _lib.SOLVER_KRYLOV:
+        raise FeastError(-1, "mixed_prec=true exists (experimental, complex64 Krylov blocks) for Krylov inner solves only: "
+                             "pass solver_opts={'kind': SOLVER_KRYLOV}; the dense LU path has no single-precision variant")
 
 
 def _densify_if_mixed(A, B):
@@ -317,7 +321,8 @@ def iter_debug_print(nit, Lam, res, contour, spurious=1e-5):
     print(line)
 
 
-def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, generalized, stats_out, comm):
+def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, generalized, stats_out, comm,
+                   mixed_prec=False):
     N, m0 = X.shape
     if A.shape[0] != A.shape[1]:
         raise ValueError("Incorrect dimensions of A, must be square")  # feast.jl:13
@@ -340,6 +345,8 @@ def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, 
         if ctx.nranks > 1:  # balanced node -> rank map (near-axis nodes cost more Krylov iterations)
             ctx.set_node_owners(node_owners(contour.nodes, ctx.nranks))
         ctx.set_solver(store=store, **solver_opts)
+        if mixed_prec:
+            ctx.set_mixed_precision(True)   # feast.jl:19-25 (experimental on the device: complex64 COCG blocks)
         ctx.set_subspace(X)
         Lam = np.zeros(m0, complex)
         res = np.zeros(m0)
@@ -387,10 +394,11 @@ def feast(X, A, contour: Contour | None = None, *, nodes=8, iter=10, c=complex(0
     Ritz vectors; returns (L[in], X[:, in], res[in]) filtered by in_contour.  `eps` is
     the reference's keyword ϵ.
     """
-    _check_plugins(factorizer, left_divider, mixed_prec)
+    _check_plugins(factorizer, left_divider, mixed_prec, solver_opts)
     if contour is None:
         contour = circular_contour_trapezoidal(c, r, nodes)  # feast.jl:6
-    return _linear_driver(X, A, None, contour, iter, eps, debug, store, ctx, solver_opts or {}, False, stats, comm)
+    return _linear_driver(X, A, None, contour, iter, eps, debug, store, ctx, solver_opts or {}, False, stats, comm,
+                          mixed_prec=bool(mixed_prec))
 
 
 def gen_feast(X, A, B, contour: Contour | None = None, *, nodes=8, iter=10, c=complex(0.0, 0.0), r=1.0,

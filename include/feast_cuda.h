@@ -195,6 +195,11 @@ FEAST_API int  feast_timer_stop(feast_ctx* ctx, float* ms);
 FEAST_API int64_t feast_launch_count(const feast_ctx* ctx);
 /* device-timed phases since the last reset (ms): [0]=project [1]=recover [2]=contour_apply */
 FEAST_API int  feast_phase_times(feast_ctx* ctx, double* ms3, int reset);
+/* EXPERIMENTAL (written after the round's GPU budget was spent, not yet run on a GPU): the reference's
+ * `mixed_prec=true` (src/feast.jl:19-25, ComplexF32 solves inside the double-precision RII loop) for the
+ * Krylov path: the COCG blocks are stored in complex64 (half the HBM traffic), arithmetic stays double.
+ * Applies when the inner solver is COCG, m0 is even and the default tile plan is in use; ignored otherwise. */
+FEAST_API int  feast_set_mixed_precision(feast_ctx* ctx, int on);
 /* Internal layout of the sparse path (no reference counterpart: UMFPACK reorders internally as
  * well).  The rows are cut into tiles whose referenced rows of the n x m0 block fit in shared
  * memory (tiled SpMM); with Krylov inner solves the rows are renumbered so that the tiles are

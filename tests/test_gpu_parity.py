@@ -600,3 +600,28 @@ def test_nlfeast_it_linear_pencil(fs):
     assert inside.sum() == want.size
     match_eigs(lam[inside], want)
     assert res[inside].max() < 1e-9
+
+
+@_experimental
+def test_feast_mixed_prec_krylov(fs):
+    """mixed_prec=true (src/feast.jl:19-25) on the Krylov path: complex64 COCG blocks inside the double-precision RII
+    loop; the eigenpairs must still meet the double-precision parity bounds (more outer iterations are allowed)."""
+    from feastsolver_jl_b200 import workloads as wl
+    from feastsolver_jl_b200 import _lib
+    m = 14
+    A, _ = wl.laplacian3d_pencil(m)
+    n = m ** 3
+    ev = np.sort(np.linalg.eigvalsh(A.toarray()))
+    c = 0.5 * (ev[0] + 0.5 * (ev[9] + ev[10]))
+    r = 0.5 * (ev[9] + ev[10]) - c
+    X0 = wl.rand_subspace(n, 24, seed=0)
+    want = ev[np.abs(ev - c) <= r]
+    st, st32 = {}, {}
+    opts = {"kind": _lib.SOLVER_KRYLOV, "inner_tol": 1e-5}
+    e64, _, r64 = fs.feast(X0.copy(), A, fs.circular_contour_gauss(c, r, 16), eps=1e-11, iter=15, solver_opts=opts, stats=st)
+    e32, _, r32 = fs.feast(X0.copy(), A, fs.circular_contour_gauss(c, r, 16), eps=1e-11, iter=15, solver_opts=opts, stats=st32,
+                           mixed_prec=True)
+    assert e32.size == e64.size == want.size
+    match_eigs(e32, want.astype(complex))
+    assert r32.max() < 1e-10
+    assert len(st32["history"]) <= len(st["history"]) + 4
