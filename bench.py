@@ -235,6 +235,8 @@ def run_ours(args):
     ctx.set_contour(contour.nodes, contour.weights)
     ctx.set_node_owners(owners)
     ctx.set_solver(**solver_opts)
+    if args.mixed_prec:
+        ctx.set_mixed_precision(True)     # experimental: complex64 COCG blocks (the reference's mixed_prec=true)
     ctx.set_subspace(X0)
     layout = ctx.layout_info()
 
@@ -312,7 +314,7 @@ def run_ours(args):
         "config": {"workload": f"C2: sparse generalized Hermitian 3-D Laplacian+mass pencil, grid {grid}^3 (n={n}, "
                                f"nnz={A.nnz}), lowest slice ({cnt} eigenvalues), m0={M0}, {NODES} Gauss-Legendre nodes "
                                f"sharded over {world} GPU(s); step = one outer FEAST iteration ({NODES} node solves + RR)",
-                   "inner_solver": f"pseudo-block COCG, rel tol {INNER_TOL}", "l2_policy": "inputs (5 GB of Krylov blocks) exceed the 126 MB L2",
+                   "inner_solver": f"pseudo-block COCG, rel tol {INNER_TOL}" + (", complex64 blocks (mixed_prec, steady-state leg only)" if args.mixed_prec else ""), "l2_policy": "inputs (5 GB of Krylov blocks) exceed the 126 MB L2",
                    "node_owners": [int(o) for o in owners],
                    "layout": {"rows_renumbered": layout["reordered"], "spmm_tiles": layout["ntiles"],
                               "halo_rows_per_row": round(layout["halo_rows_per_row"], 3)}},
@@ -347,6 +349,8 @@ def main():
     ap.add_argument("--grid", type=int, default=GRID, help="grid points per dimension (default: the C2 size 100)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
+    ap.add_argument("--mixed-prec", action="store_true",
+                    help="EXPERIMENTAL: complex64 storage of the COCG blocks in the steady-state leg (not the headline configuration)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 0)
