@@ -18,6 +18,7 @@ ap.add_argument("--iter", type=int, default=12)
 ap.add_argument("--tol", type=float, default=1e-8)
 ap.add_argument("--maxit", type=int, default=2000)
 ap.add_argument("--solver", default="auto", choices=["auto", "dense", "krylov"])
+ap.add_argument("--no-store", action="store_true", help="refactor at every outer iteration (store=false)")
 a = ap.parse_args()
 coeffs = wl.butterfly_coeffs(a.mb)
 n = a.mb ** 2
@@ -25,7 +26,7 @@ X0 = wl.rand_subspace(n, a.m0, seed=0)
 kind = {"auto": _lib.SOLVER_AUTO, "dense": _lib.SOLVER_DENSE_LU, "krylov": _lib.SOLVER_KRYLOV}[a.solver]
 st = {}
 t0 = time.perf_counter()
-lam, X, res = fs.nlfeast(coeffs, X0, a.nodes, a.iter, c=1 + 1j, r=a.r, eps=1e-10, stats=st,
+lam, X, res = fs.nlfeast(coeffs, X0, a.nodes, a.iter, c=1 + 1j, r=a.r, eps=1e-10, stats=st, store=not a.no_store,
                          solver_opts={"kind": kind, "inner_tol": a.tol, "max_inner": a.maxit})
 tts = time.perf_counter() - t0
 inside = np.abs(lam - (1 + 1j)) <= a.r

@@ -13,4 +13,4 @@ done
 timeout 300 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --mixed-prec 2>&1 | tail -2
 timeout 300 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu 2>&1 | tail -2
 # 4. C4 at full size with the pivoted band LU (store=false: 8.2 GB of factors per node do not fit 24 nodes on one GPU)
-# FEAST_BAND_PIVOT=1 timeout 900 python scripts/c4_run.py --mb 500 --m0 64 --nodes 24 --r 0.006 --iter 4
+# FEAST_BAND_PIVOT=1 timeout 900 python scripts/c4_run.py --mb 500 --m0 64 --nodes 24 --r 0.006 --iter 4 --no-store
