@@ -55,6 +55,12 @@ void dev_free(T*& p) {
     p = nullptr;
 }
 
+bool create_ctx_events(feast_ctx* ctx) {   // on the context's device (cudaSetDevice was called by the caller)
+    for (auto& e : ctx->evn) if (cudaEventCreate(&e) != cudaSuccess) return false;
+    for (auto& e : ctx->evk) if (cudaEventCreate(&e) != cudaSuccess) return false;
+    return true;
+}
+
 int bind_device(feast_ctx* ctx) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return 0;
@@ -65,6 +71,13 @@ void free_operator(Operator& op) {
     dev_free(op.uvals_r);
     dev_free(op.uvals_c);
     op = Operator();
+}
+
+void drop_stored_factors(feast_ctx* ctx) {
+    for (auto& f : ctx->stored) { dev_free(f.lu); dev_free(f.ipiv); dev_free(f.perm); dev_free(f.dinv); }
+    ctx->stored.clear();
+    for (auto& f : ctx->bstored) band_free(f);
+    ctx->bstored.clear();
 }
 
 void free_problem_derived(feast_ctx* ctx) {
@@ -82,10 +95,7 @@ void free_problem_derived(feast_ctx* ctx) {
     dev_free(ctx->zdense);
     dev_free(ctx->zpiv);
     dev_free(ctx->zdinv);
-    for (auto& f : ctx->stored) { dev_free(f.lu); dev_free(f.ipiv); dev_free(f.perm); dev_free(f.dinv); }
-    ctx->stored.clear();
-    for (auto& f : ctx->bstored) band_free(f);
-    ctx->bstored.clear();
+    drop_stored_factors(ctx);
     band_free(ctx->bscratch);
     dev_free(ctx->band_tmp);
     ctx->band_tmp_elems = 0;
@@ -611,6 +621,7 @@ int solve_shifted(feast_ctx* ctx, int solver, int method, int k, const hc128* co
         st.inner_iters_total += steps;                                  // refinement steps
         st.inner_iters_max = std::max(st.inner_iters_max, steps);
         st.inner_relres_max = std::max(st.inner_relres_max, rel);
+        if (!(rel <= ctx->inner_tol)) *rc_final = FEAST_WARN_INNER_MAXIT;   // stagnated or non-finite refinement: tell the caller
     } else {
         FEAST_TRY(assemble_sparse_Z(ctx, coef, ctx->zvals));
         if (e1) cudaEventRecord(e1, ctx->stream);
@@ -669,7 +680,7 @@ int feast_ctx_create(feast_ctx** out, int device) {
     feast_ctx* ctx = new feast_ctx();
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess || !create_ctx_events(ctx)) {
         int rc = feast_fail(nullptr, FEAST_ERR_CUDA, "context creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         delete ctx;
         return rc;
@@ -690,6 +701,8 @@ int feast_ctx_destroy(feast_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (auto& e : ctx->evn) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->evk) if (e) cudaEventDestroy(e);
     if (ctx->sw0) cudaEventDestroy(ctx->sw0);
     if (ctx->sw1) cudaEventDestroy(ctx->sw1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -800,7 +813,7 @@ int feast_set_problem(feast_ctx* ctx, int kind, int nslots) {
 // ------------------------------------------------------------------------- contour / solver / comm
 int feast_set_contour(feast_ctx* ctx, int nnodes, const feast_c128* z, const feast_c128* w) {
     ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
-    ARG_CHECK(ctx, nnodes >= 1, 2, "need at least one node");
+    ARG_CHECK(ctx, nnodes >= 1 && nnodes <= feast_ctx::kMaxNodes, 2, "need between 1 and 4096 nodes");
     ARG_CHECK(ctx, z != nullptr, 3, "null nodes");
     ARG_CHECK(ctx, w != nullptr, 4, "null weights");
     ctx->znodes.resize(nnodes);
@@ -811,8 +824,7 @@ int feast_set_contour(feast_ctx* ctx, int nnodes, const feast_c128* z, const fea
     for (int k = 0; k < nnodes; ++k) ctx->owner[k] = k % ctx->nranks;
     ctx->node_cost.assign(nnodes, 0.0);
     ctx->have_costs = false;
-    for (auto& f : ctx->stored) { dev_free(f.lu); dev_free(f.ipiv); dev_free(f.perm); dev_free(f.dinv); }
-    ctx->stored.clear();
+    drop_stored_factors(ctx);   // the factors belong to the old nodes
     return 0;
 }
 
@@ -822,6 +834,7 @@ int feast_set_solver(feast_ctx* ctx, int kind, int krylov, double inner_tol, int
     ARG_CHECK(ctx, krylov >= 0 && krylov <= 3, 3, "unknown Krylov method");
     ARG_CHECK(ctx, inner_tol > 0 && inner_tol < 1, 4, "inner_tol must be in (0,1)");
     ARG_CHECK(ctx, max_inner >= 1, 5, "max_inner must be positive");
+    if ((store != 0) != (ctx->store != 0) || kind != ctx->solver) drop_stored_factors(ctx);
     ctx->solver = kind; ctx->krylov = krylov; ctx->inner_tol = inner_tol; ctx->max_inner = max_inner; ctx->store = store;
     // the internal row ordering follows the solver kind (Krylov: tiled; direct: natural).  A change after
     // feast_set_problem rebuilds the device operators from the host copies and drops the subspace blocks.
@@ -902,7 +915,7 @@ int feast_set_subspace(feast_ctx* ctx, int64_t n, int m0, const feast_c128* X, i
         free_blocks(ctx);
         ctx->m0 = m0;
         FEAST_TRY(dev_alloc(ctx, &ctx->stage, (size_t)n * m0));
-        FEAST_TRY(dev_alloc(ctx, &ctx->small_d, (size_t)4 * m0 * m0 + 16 * (size_t)m0 + 64));
+        FEAST_TRY(dev_alloc(ctx, &ctx->small_d, feast_ctx::small_elems(m0)));
         // reduction scratch: split-K Gram partials (2*148 slices of m0 x m0) or SpMM/col-dot partials
         size_t red = std::max((size_t)2 * kNumSMs * m0 * m0 * sizeof(c128), spmm_partials_bytes(m0));
         red = std::max(red, (size_t)kNumSMs * 4 * 3 * (size_t)std::max(m0, 256) * sizeof(double));
@@ -983,8 +996,8 @@ int feast_recover_residual(feast_ctx* ctx, const feast_c128* Xq, const feast_c12
     const int m = ctx->m0;
     PhaseTimer tm(ctx, 1);
     c128* M_d = ctx->small_d;
-    c128* lam_d = ctx->small_d + (size_t)2 * m * m;
-    double* nrm_d = (double*)(ctx->small_d + (size_t)3 * m * m);
+    c128* lam_d = ctx->vec_lam();
+    double* nrm_d = ctx->vec_nrm();
     double* fro_d = nrm_d + m;
     CUDA_TRY(ctx, cudaMemcpyAsync(M_d, Xq, sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(lam_d, lambda, sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
@@ -1062,15 +1075,14 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
     if (solver == FEAST_SOLVER_KRYLOV) FEAST_TRY(ensure_krylov_work(ctx, method));
     feast_stats st;
     memset(&st, 0, sizeof(st));
-    cudaEvent_t e0, e1, e2, e3;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
+    cudaEvent_t e0 = ctx->evn[0], e1 = ctx->evn[1], e2 = ctx->evn[2], e3 = ctx->evn[3];   // owned by the context
     PhaseTimer tm(ctx, 2);
     int rc_final = 0;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->Q.p, 0, sizeof(c128) * n * m, ctx->stream));           // feast.jl:58
     if (poly) CUDA_TRY(ctx, cudaMemsetAsync(ctx->Q1.p, 0, sizeof(c128) * n * m, ctx->stream)); // nlfeast.jl:32-33
     const int nnodes = (int)ctx->znodes.size();
     if (ctx->store && (int)ctx->stored.size() != nnodes) ctx->stored.resize(nnodes);
-    c128* d_d = ctx->small_d + (size_t)3 * m * m;
+    c128* d_d = ctx->vec_d();
     std::vector<hc128> d(m);
     hc128 coef[FEAST_MAX_SLOTS];
     const c128* rhs = first_pass ? ctx->X.p : ctx->R.p;
@@ -1110,7 +1122,7 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
         if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclAllReduce: %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
         cudaEventRecord(e3, ctx->stream);
         if (can_move_nodes) {   // share the measured per-node costs (nnodes doubles) for the next pass
-            double* cbuf = (double*)(ctx->small_d + (size_t)3 * m * m);
+            double* cbuf = ctx->vec_cost();
             CUDA_TRY(ctx, cudaMemcpyAsync(cbuf, cost_local.data(), sizeof(double) * nnodes, cudaMemcpyHostToDevice, ctx->stream));
             rc = api->AllReduce(cbuf, cbuf, (size_t)nnodes, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
             if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclAllReduce (node costs) failed");
@@ -1123,12 +1135,11 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
         st.t_reduce_ms = c;
     }
     st.t_total_ms = tm.stop();
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     if (stats) *stats = st;
     if (st.info) return feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d of a shifted factorisation", st.info);
     if (rc_final == FEAST_WARN_INNER_MAXIT)
-        feast_fail(ctx, FEAST_WARN_INNER_MAXIT, "Krylov inner solve stopped at max_inner=%d (relres %.3e)", ctx->max_inner,
-                   st.inner_relres_max);
+        feast_fail(ctx, FEAST_WARN_INNER_MAXIT, "inner solve did not reach inner_tol=%.1e (max_inner=%d, relres %.3e)", ctx->inner_tol,
+                   ctx->max_inner, st.inner_relres_max);
     return rc_final;
 }
 
@@ -1264,9 +1275,9 @@ int feast_dual_recover_residual(feast_ctx* ctx, const feast_c128* Xqr, const fea
     PhaseTimer tm(ctx, 1);
     FEAST_TRY(ensure_block(ctx, ctx->W1));
     c128* M_d = ctx->small_d;
-    c128* lam_d = ctx->small_d + (size_t)2 * m * m;
-    c128* lamc_d = lam_d + m;
-    double* nrm_d = (double*)(ctx->small_d + (size_t)3 * m * m);
+    c128* lam_d = ctx->vec_lam();
+    c128* lamc_d = ctx->vec_lamc();
+    double* nrm_d = ctx->vec_nrm();
     std::vector<hc128> lamc(m);
     for (int j = 0; j < m; ++j) lamc[j] = hc128(lambda[j].re, -lambda[j].im);
     CUDA_TRY(ctx, cudaMemcpyAsync(lam_d, lambda, sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
@@ -1319,8 +1330,8 @@ int feast_dual_contour_apply(feast_ctx* ctx, const feast_c128* lambda, feast_sta
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->Ql.p, 0, sizeof(c128) * n * m, ctx->stream));
     const int nnodes = (int)ctx->znodes.size();
     if (ctx->store && (int)ctx->stored.size() != nnodes) ctx->stored.resize(nnodes);
-    c128* d_d = ctx->small_d + (size_t)3 * m * m;
-    c128* dl_d = d_d + m;
+    c128* d_d = ctx->vec_d();
+    c128* dl_d = ctx->vec_dl();
     std::vector<hc128> d(m), dl(m);
     hc128 coef[FEAST_MAX_SLOTS];
     for (int k = 0; k < nnodes; ++k) {

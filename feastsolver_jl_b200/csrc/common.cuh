@@ -83,15 +83,11 @@ struct DenseLU {             // one stored factorisation (column-major, LAPACK g
     int64_t n = 0;
 };
 
-struct BandFactor {          // block-tridiagonal LU of a banded operator (band.cu): Schur complements S_I factored densely
+struct BandFactor {          // band LU with partial pivoting across adjacent block rows (band.cu)
     int b = 0, nbk = 0;      // block size (>= half bandwidth) and number of block rows
-    c128* lu = nullptr;      // [nbk][b*b] row-major LU of S_I
-    int* piv = nullptr;      // [nbk][2*b] ipiv then perm
-    c128* dinv = nullptr;    // [nbk][2*b*kDiagNB] diagonal-block inverses of each S_I
-    // pivoted variant (band_factor_pivoted: partial pivoting across adjacent block rows, EXPERIMENTAL, FEAST_BAND_PIVOT=1):
-    // lu = [nbk][b*b] L11\U11 of each 2b x b panel (last block: LU of the final Schur complement), piv = [nbk][2*b]
-    // (window-relative interchanges, then the perm of the last block)
-    bool pivoted = false;
+    c128* lu = nullptr;      // [nbk][b*b] row-major L11\U11 of each 2b x b panel (last block: LU of the final Schur complement)
+    int* piv = nullptr;      // [nbk][2*b] window-relative interchanges (last block: ipiv then perm)
+    c128* dinv = nullptr;    // [2*b*kDiagNB] diagonal-block inverses of the last block
     c128* l21 = nullptr;     // [nbk][b*b] multipliers of the lower half of each panel
     c128* u12 = nullptr;     // [nbk][b*2b] row-major (ld 2b): the U rows of block columns I+1, I+2
 };
@@ -172,7 +168,19 @@ struct feast_ctx {
     void* gm_small = nullptr;     // GMRES per-column Hessenberg / rotations
     int gm_restart = 0;
     c128* stage = nullptr;        // n x m0 column-major staging (uploads / downloads)
-    c128* small_d = nullptr;      // device scratch for m0 x m0 matrices (4 of them) + scalars
+    // device scratch: [4 m0^2: m0 x m0 matrices][16 m0 + 64: Krylov per-column scalars (krylov.cu carve_scalars)]
+    // [6 m0: lambda, conj(lambda), d, dl, 2 m0 doubles of norms][kMaxNodes doubles: node costs].  Every user has its own
+    // region (round 1 carved lambda / d / the cost buffer out of the matrix area, which overlapped for m0 == 1).
+    c128* small_d = nullptr;
+    static constexpr int kMaxNodes = 4096;
+    static size_t small_elems(int m) { return (size_t)4 * m * m + 16 * (size_t)m + 64 + 6 * (size_t)m + kMaxNodes / 2 + 16; }
+    c128* vec_base() const { return small_d + (size_t)4 * m0 * m0 + 16 * (size_t)m0 + 64; }
+    c128* vec_lam() const { return vec_base(); }
+    c128* vec_lamc() const { return vec_base() + m0; }
+    c128* vec_d() const { return vec_base() + 2 * (size_t)m0; }
+    c128* vec_dl() const { return vec_base() + 3 * (size_t)m0; }
+    double* vec_nrm() const { return (double*)(vec_base() + 4 * (size_t)m0); }   // 4 m0 doubles
+    double* vec_cost() const { return (double*)(vec_base() + 6 * (size_t)m0 + 8); }
     double* red_d = nullptr;      // reduction partials
     size_t red_bytes = 0;
     void* pinned = nullptr;       // pinned host scratch
@@ -186,6 +194,8 @@ struct feast_ctx {
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t sw0 = nullptr, sw1 = nullptr;   // user stopwatch (feast_timer_*)
+    cudaEvent_t evn[4] = {nullptr, nullptr, nullptr, nullptr};   // per-node factor / solve brackets of the contour loop
+    cudaEvent_t evk[32] = {};                   // SpMM brackets inside the Krylov solves (read back at the convergence checks)
     double phase_ms[3] = {0, 0, 0};
 };
 

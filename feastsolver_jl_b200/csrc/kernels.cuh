@@ -85,7 +85,7 @@ int dense_getrs(feast_ctx* ctx, int64_t n, const c128* LU, const int* perm_d, co
 // ---- band.cu: block-tridiagonal direct solver for banded sparse operators
 struct BandFactor;
 int band_factor(feast_ctx* ctx, const c128* zvals, BandFactor& F, int* info);
-int band_solve(feast_ctx* ctx, const BandFactor& F, const c128* zvals, int m, const c128* Rhs, c128* Y);
+int band_solve(feast_ctx* ctx, const BandFactor& F, int m, const c128* Rhs, c128* Y);
 void band_free(BandFactor& F);
 // band_solve + iterative refinement against the assembled sparse operator (work: n x m scratch)
 int band_solve_refined(feast_ctx* ctx, const BandFactor& F, const c128* zvals, int m, const c128* Rhs, c128* Y, c128* work,

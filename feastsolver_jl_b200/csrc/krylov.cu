@@ -307,10 +307,7 @@ int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs,
     hf->relmax = 1.0;
     // SpMM launches are bracketed by events (read back at the convergence checks): this is
     // the kernel bench.py reports the HBM roofline for, timed inside the real solve.
-    constexpr int kEv = 2 * 16;
-    static thread_local cudaEvent_t evs[kEv];
-    static thread_local bool evs_ready = false;
-    if (!evs_ready) { for (int i = 0; i < kEv; ++i) cudaEventCreate(&evs[i]); evs_ready = true; }
+    cudaEvent_t* evs = ctx->evk;   // 2 x 16, created with the context on its device
     int ev_n = 0;
     double spmm_ms = 0.0;
     int spmm_launches = 0;

@@ -216,15 +216,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    // bounded spin: a transaction-count mismatch must fail the launch (trap -> cudaErrorLaunchFailure), not hang the device
+    uint32_t done = 0;
+    for (uint32_t spins = 0; spins < (1u << 26); ++spins) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    asm volatile("trap;");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -362,12 +365,12 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
     }
 }
 
-// ------------------------------------------------------------------ mixed-precision variant (EXPERIMENTAL)
+// ------------------------------------------------------------------ mixed-precision variant
 // Same tiled kernel for blocks stored in complex64 (the reference's `mixed_prec=true`: ComplexF32 solves inside the
 // double-precision RII loop, src/feast.jl:19-25).  A 16-byte unit of a row holds TWO complex64 columns, so the copy
 // geometry is the one of the complex128 kernel with half as many units per row (m0 = 64 -> one slab of 32 units, one
 // pass per tile); products and the fused <p, Zp> accumulate in double, the operator values stay complex128.
-// NOT YET RUN ON A GPU (written after the round's GPU budget was spent): reachable only through feast_set_mixed_precision.
+// First run on a B200 in round 2 (profiles/r2_round2_validate.log); reachable through feast_set_mixed_precision.
 template <bool DOT, typename CFG>
 __global__ void __launch_bounds__(CFG::kThreads, CFG::kCtas)
 spmm_tiled_f32_kernel(int mu, int ntiles, const int* __restrict__ t_ptr, const int* __restrict__ t_hptr,
@@ -452,11 +455,12 @@ spmm_tiled_f32_kernel(int mu, int ntiles, const int* __restrict__ t_ptr, const i
                     }
                 }
                 if (g < SW) {
-                    Y[(int64_t)(r0 + lr) * ldy + j0 + g] = make_float4((float)acc0.x, (float)acc0.y, (float)acc1.x, (float)acc1.y);
-                    if (DOT) {
+                    const float4 qv = make_float4((float)acc0.x, (float)acc0.y, (float)acc1.x, (float)acc1.y);
+                    Y[(int64_t)(r0 + lr) * ldy + j0 + g] = qv;
+                    if (DOT) {   // <p, q> of the q that is STORED (the recurrence continues from the rounded block)
                         const float4 own = xs[(size_t)lr * SW + g];
-                        cfma(dacc[s][0], cmake((double)own.x, (double)own.y), acc0);
-                        cfma(dacc[s][1], cmake((double)own.z, (double)own.w), acc1);
+                        cfma(dacc[s][0], cmake((double)own.x, (double)own.y), cmake((double)qv.x, (double)qv.y));
+                        cfma(dacc[s][1], cmake((double)own.z, (double)own.w), cmake((double)qv.z, (double)qv.w));
                     }
                 }
             }

@@ -153,15 +153,14 @@ def test_banded_block_tridiagonal_solver(fs):
     assert np.abs(Z @ Y - Bm).max() <= 1e-11 * np.abs(Bm).max() * np.abs(Z).sum(axis=1).max()
 
 
-@pytest.mark.skipif(not os.environ.get("FEAST_RUN_EXPENSIVE"), reason="~1 min on a B200; set FEAST_RUN_EXPENSIVE=1")
 def test_banded_solver_backward_error_many_block_rows(fs):
-    """Normwise backward error of the block-tridiagonal elimination on the C4 operator with many block rows
-    (default 200 x 200 one-dimensional blocks; FEAST_BAND_MB overrides).  Measured in round 1: 6e-17 up to 300 x 300 blocks,
-    4e-13 at 400, 2e-3 at 500 -- the elimination pivots inside the Schur complements only and its element growth is what stalls
-    C4 at 500 x 500 (profiles/r1b_c4_full_n250000.json); a band LU with pivoting across block rows is the planned fix."""
+    """Normwise backward error of the band LU on the C4 operator with many block rows (default 400 x 400 one-dimensional
+    blocks, n = 160 000, ~7 s on a B200; FEAST_BAND_MB overrides).  The round-1 elimination, which pivoted inside the Schur
+    complements only, measured 4e-13 at 400 and 2e-3 at 500 blocks (what stalled C4 at n = 250 000); the band LU with
+    partial pivoting across adjacent block rows measures 1.1e-16 at 400 and 3.7e-16 at 500 (profiles/r2_round2_validate.log)."""
     from feastsolver_jl_b200 import workloads as wl
     from feastsolver_jl_b200 import _lib
-    mb = int(os.environ.get("FEAST_BAND_MB", "200"))
+    mb = int(os.environ.get("FEAST_BAND_MB", "400"))
     coeffs = wl.butterfly_coeffs(mb)
     n = mb * mb
     z = 1 + 1j + (3.0 / mb) * np.exp(1j * np.pi / 24)
@@ -347,9 +346,12 @@ def test_C2_reduced_sparse_generalized(fs, solver):
     assert np.abs(np.linalg.norm(Rchk, axis=0) - rg).max() < 1e-12
 
 
-def test_generalized_nonsymmetric_sparse_bicgstab(fs):
-    """Non-symmetric sparse A exercises the BiCGStab inner solver."""
+@pytest.mark.parametrize("method", ["gmres_auto", "bicgstab"])
+def test_generalized_nonsymmetric_sparse_krylov(fs, method):
+    """Non-symmetric sparse A: KRYLOV_AUTO selects restarted GMRES (api.cu effective_krylov); KRYLOV_BICGSTAB forces the
+    pseudo-block BiCGStab recurrences of krylov.cu (the reference's own inexact-solve precedent is bicgstabl)."""
     from feastsolver_jl_b200 import _lib
+    kry = _lib.KRYLOV_AUTO if method == "gmres_auto" else _lib.KRYLOV_BICGSTAB
     n = 400
     rng = np.random.default_rng(5)
     d = np.linspace(1.0, 40.0, n)
@@ -360,7 +362,7 @@ def test_generalized_nonsymmetric_sparse_bicgstab(fs):
     X0 = x0(n, 24, 9)
     eo, vo, ro = fo.gen_feast(X0.copy(), A, B, ct_o, iter=30)
     eg, vg, rg = fs.gen_feast(X0.copy(), A, B, ct_g, iter=30,
-                              solver_opts={"kind": _lib.SOLVER_KRYLOV, "inner_tol": 1e-10, "max_inner": 2000})
+                              solver_opts={"kind": _lib.SOLVER_KRYLOV, "krylov": kry, "inner_tol": 1e-10, "max_inner": 2000})
     assert ro.max() < 1e-12  # the oracle itself converged, so the comparison is meaningful
     match_eigs(eg, eo)
     assert rg.max() <= 10 * max(ro.max(), 1e-12)
@@ -560,12 +562,7 @@ def test_empty_contour_returns_empty(fs, capsys):
 
 
 # ----------------------------------------------------------------------------- inexact-inner-solve drivers
-# Written after the round's GPU budget was spent: they compose validated pieces (linear / polynomial drivers with Krylov
-# inner solves) but have not run on a GPU yet, hence gated.  FEAST_RUN_EXPERIMENTAL=1 runs them.
-_experimental = pytest.mark.skipif(not os.environ.get("FEAST_RUN_EXPERIMENTAL"), reason="not yet validated on a GPU")
-
-
-@_experimental
+# First run on a B200 at the start of round 2 (profiles/r2_round2_validate.log); part of the default GPU suite since.
 def test_ifeast_matches_oracle(fs):
     """ifeast! (src/feast_experimental.jl:1-60): all m0 Ritz pairs after `iter` passes with inexact solves."""
     n, m0 = 2000, 12
@@ -585,7 +582,6 @@ def test_ifeast_matches_oracle(fs):
         fs.ifeast(A.toarray(), X0, 8, 1)
 
 
-@_experimental
 def test_nlfeast_it_linear_pencil(fs):
     """nlfeast_it! (src/nlfeast.jl:87-171) on T(z) = zI - A with Krylov inner solves (1e-3, then 1e-8)."""
     n, m0 = 2000, 10
@@ -602,7 +598,6 @@ def test_nlfeast_it_linear_pencil(fs):
     assert res[inside].max() < 1e-9
 
 
-@_experimental
 def test_feast_mixed_prec_krylov(fs):
     """mixed_prec=true (src/feast.jl:19-25) on the Krylov path: complex64 COCG blocks inside the double-precision RII
     loop; the eigenpairs must still meet the double-precision parity bounds (more outer iterations are allowed)."""
@@ -612,10 +607,11 @@ def test_feast_mixed_prec_krylov(fs):
     A, _ = wl.laplacian3d_pencil(m)
     n = m ** 3
     ev = np.sort(np.linalg.eigvalsh(A.toarray()))
-    c = 0.5 * (ev[0] + 0.5 * (ev[9] + ev[10]))
-    r = 0.5 * (ev[9] + ev[10]) - c
+    lo, hi = ev[0] - 0.4 * (ev[1] - ev[0]), 0.5 * (ev[9] + ev[10])   # both edges inside spectral gaps (round 1 put ev[0] ON the circle)
+    c, r = 0.5 * (lo + hi), 0.5 * (hi - lo)
     X0 = wl.rand_subspace(n, 24, seed=0)
     want = ev[np.abs(ev - c) <= r]
+    assert want.size == 10
     st, st32 = {}, {}
     opts = {"kind": _lib.SOLVER_KRYLOV, "inner_tol": 1e-5}
     e64, _, r64 = fs.feast(X0.copy(), A, fs.circular_contour_gauss(c, r, 16), eps=1e-11, iter=15, solver_opts=opts, stats=st)
