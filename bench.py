@@ -224,7 +224,8 @@ def run_ours(args):
     contour = fs.circular_contour_gauss(c, r, NODES)
     hook = make_comm_hook()
     owners = node_owners(contour.nodes, world)
-    solver_opts = {"kind": _lib.SOLVER_KRYLOV, "inner_tol": INNER_TOL, "max_inner": MAX_INNER}
+    solver_opts = {"kind": _lib.SOLVER_KRYLOV, "inner_tol": INNER_TOL, "max_inner": MAX_INNER,
+                   "precond": {"auto": _lib.PRECOND_AUTO, "none": _lib.PRECOND_NONE, "amg": _lib.PRECOND_AMG}[args.precond]}
 
     ctx = fs.FeastContext(device=local)
     ctx.set_operator(0, A)
@@ -239,6 +240,7 @@ def run_ours(args):
         ctx.set_mixed_precision(True)     # experimental: complex64 COCG blocks (the reference's mixed_prec=true)
     ctx.set_subspace(X0)
     layout = ctx.layout_info()
+    pinfo = ctx.preconditioner_info()
 
     for _ in range(args.warmup):
         outer_iteration(fs, ctx, contour)
@@ -270,7 +272,8 @@ def run_ours(args):
     if args.no_e2e:
         if rank == 0:
             print(json.dumps({"metric": "contour_node_solves_per_sec", "value": value, "ms_per_step": ms / args.steps,
-                              "spmm_ms_per_launch": spmm_ms, "gpu_launches": launches, "note": "profiling run (--no-e2e)"}))
+                              "spmm_ms_per_launch": spmm_ms, "gpu_launches": launches, "inner_iters_per_step": inner_total / args.steps,
+                              "preconditioner": pinfo, "note": "profiling run (--no-e2e)"}))
         if world > 1:
             dist.destroy_process_group()
         return
@@ -349,6 +352,8 @@ def main():
     ap.add_argument("--grid", type=int, default=GRID, help="grid points per dimension (default: the C2 size 100)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
+    ap.add_argument("--precond", default="auto", choices=["auto", "none", "amg"],
+                    help="Krylov preconditioner (auto: smoothed-aggregation V-cycle when applicable)")
     ap.add_argument("--mixed-prec", action="store_true",
                     help="EXPERIMENTAL: complex64 storage of the COCG blocks in the steady-state leg (not the headline configuration)")
     args = ap.parse_args()

@@ -18,7 +18,8 @@ FEAST_ERR_CUDA, FEAST_ERR_NCCL, FEAST_ERR_OOM, FEAST_ERR_STATE, FEAST_ERR_SINGUL
 FEAST_WARN_INNER_MAXIT = 2000
 SOLVER_AUTO, SOLVER_DENSE_LU, SOLVER_KRYLOV, SOLVER_BANDED_LU = 0, 1, 2, 3
 KRYLOV_AUTO, KRYLOV_COCG, KRYLOV_BICGSTAB, KRYLOV_GMRES = 0, 1, 2, 3
-PROBLEM_STANDARD, PROBLEM_GENERALIZED, PROBLEM_POLYNOMIAL = 0, 1, 2
+PROBLEM_STANDARD, PROBLEM_GENERALIZED, PROBLEM_POLYNOMIAL, PROBLEM_SAMPLED = 0, 1, 2, 3
+PRECOND_NONE, PRECOND_AMG, PRECOND_AUTO = 0, 1, 2
 MAX_SLOTS = 8
 
 
@@ -30,7 +31,7 @@ class FeastStats(C.Structure):
     _fields_ = [("nodes_local", C.c_int), ("inner_iters_total", C.c_int), ("inner_iters_max", C.c_int),
                 ("info", C.c_int), ("inner_relres_max", C.c_double), ("t_factor_ms", C.c_double),
                 ("t_solve_ms", C.c_double), ("t_reduce_ms", C.c_double), ("t_total_ms", C.c_double),
-                ("t_spmm_ms", C.c_double), ("spmm_launches", C.c_int64)]
+                ("t_spmm_ms", C.c_double), ("spmm_launches", C.c_int64), ("precond_levels", C.c_int), ("reserved0", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -72,6 +73,11 @@ SIGNATURES = {
     "feast_project": (_i, [_vp, _vp, _vp]),
     "feast_recover_residual": (_i, [_vp, _vp, _vp, _vp]),
     "feast_contour_apply": (_i, [_vp, _vp, _i, C.POINTER(FeastStats)]),
+    "feast_set_sample_dense": (_i, [_vp, _i64, _vp, _i64, _i]),
+    "feast_set_sample_csc": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _i]),
+    "feast_contour_node": (_i, [_vp, _i, _vp, _i, _i, C.POINTER(FeastStats)]),
+    "feast_node_needs_sample": (_i, [_vp, _i]),
+    "feast_sampled_residual": (_i, [_vp, _i, _d, C.POINTER(C.c_double)]),
     "feast_beyn_reduce": (_i, [_vp, _vp, _vp]),
     "feast_orthonormalize_X": (_i, [_vp]),
     "feast_dual_set_subspace": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _i64]),
@@ -91,7 +97,13 @@ SIGNATURES = {
     "feast_launch_count": (_i64, [_vp]),
     "feast_phase_times": (_i, [_vp, _vp, _i]),
     "feast_set_mixed_precision": (_i, [_vp, _i]),
+    "feast_set_preconditioner": (_i, [_vp, _i]),
+    "feast_preconditioner_info": (_i, [_vp, C.POINTER(_i), _vp, _i, C.POINTER(C.c_double)]),
     "feast_layout_info": (_i, [_vp, _vp, C.POINTER(C.c_double)]),
+    "feast_debug_amg_build": (_vp, [_i64, _vp, _vp, _i, _vp, _i, C.POINTER(_i), C.POINTER(C.c_double)]),
+    "feast_debug_amg_level_info": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_double)]),
+    "feast_debug_amg_level_get": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "feast_debug_amg_free": (None, [_vp]),
     "feast_debug_cholqr": (_i, [_i64, _i, _vp, _i64, _vp, C.POINTER(_i)]),
     "feast_debug_tile_plan": (_i, [_i64, _vp, _vp, _i, _i, _i, _i, _i, _vp, C.POINTER(_i), C.POINTER(C.c_double)]),
 }

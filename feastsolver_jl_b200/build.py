@@ -17,8 +17,8 @@ OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libfeast_cuda.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["api.cu", "spmm.cu", "blockops.cu", "zgemm_dmma.cu", "krylov.cu", "dense.cu", "band.cu"]
-CPP_SOURCES = ["contour.cpp", "nccl_dl.cpp", "reorder.cpp"]
+CU_SOURCES = ["api.cu", "spmm.cu", "blockops.cu", "zgemm_dmma.cu", "krylov.cu", "dense.cu", "band.cu", "amg.cu"]
+CPP_SOURCES = ["contour.cpp", "nccl_dl.cpp", "reorder.cpp", "amg_setup.cpp"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 
@@ -63,7 +63,7 @@ def build(force=False, verbose=False):
                 if rc != 0:
                     raise RuntimeError(f"nvcc failed on {src}")
     if jobs or not os.path.exists(LIB):
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "--cudart=static", "-ldl",
+        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fPIC", "--cudart=static", "-ldl", "-lpthread",
                "-Xlinker", "--exclude-libs,ALL"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

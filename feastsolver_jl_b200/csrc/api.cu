@@ -80,7 +80,9 @@ void drop_stored_factors(feast_ctx* ctx) {
     ctx->bstored.clear();
 }
 
-void free_problem_derived(feast_ctx* ctx) {
+// everything derived from the sparsity pattern and the slot values (device layout of the sparse path)
+void free_pattern(feast_ctx* ctx) {
+    amg_free(ctx);               // level 0 aliases the union pattern freed below
     dev_free(ctx->u_rowptr);
     dev_free(ctx->u_col);
     dev_free(ctx->perm_d);
@@ -92,6 +94,11 @@ void free_problem_derived(feast_ctx* ctx) {
     ctx->tiles_ok = false;
     ctx->ntiles = 0;
     dev_free(ctx->zvals);
+    for (int i = 0; i < FEAST_MAX_SLOTS; ++i) { dev_free(ctx->ops[i].uvals_r); dev_free(ctx->ops[i].uvals_c); }
+}
+
+void free_problem_derived(feast_ctx* ctx) {
+    free_pattern(ctx);
     dev_free(ctx->zdense);
     dev_free(ctx->zpiv);
     dev_free(ctx->zdinv);
@@ -99,7 +106,6 @@ void free_problem_derived(feast_ctx* ctx) {
     band_free(ctx->bscratch);
     dev_free(ctx->band_tmp);
     ctx->band_tmp_elems = 0;
-    for (int i = 0; i < FEAST_MAX_SLOTS; ++i) { dev_free(ctx->ops[i].uvals_r); dev_free(ctx->ops[i].uvals_c); }
     ctx->problem_ready = false;
 }
 
@@ -211,8 +217,20 @@ int effective_solver(const feast_ctx* ctx);
 // Direct solvers keep the natural ordering (the banded one relies on it).  FEAST_REORDER=0 disables.
 bool want_reorder(const feast_ctx* ctx) {
     static const bool off = getenv("FEAST_REORDER") && atoi(getenv("FEAST_REORDER")) == 0;
-    if (off || ctx->storage_dense) return false;
+    if (off || ctx->storage_dense || ctx->problem == FEAST_PROBLEM_SAMPLED) return false;   // samples change the pattern: natural order
     return effective_solver(ctx) == FEAST_SOLVER_KRYLOV;
+}
+
+// The multigrid preconditioner applies to COCG on linear problems whose slots are all real and symmetric.
+bool want_amg(const feast_ctx* ctx) {
+    static const int64_t min_n = getenv("FEAST_AMG_MIN_N") ? atoll(getenv("FEAST_AMG_MIN_N")) : 20000;
+    if (ctx->precond == FEAST_PRECOND_NONE || ctx->storage_dense) return false;
+    if (ctx->problem != FEAST_PROBLEM_STANDARD && ctx->problem != FEAST_PROBLEM_GENERALIZED) return false;
+    if (effective_solver(ctx) != FEAST_SOLVER_KRYLOV || !ctx->all_symmetric) return false;
+    if (ctx->krylov != FEAST_KRYLOV_AUTO && ctx->krylov != FEAST_KRYLOV_COCG) return false;
+    for (int s = 0; s < ctx->nslots; ++s)
+        if (ctx->ops[s].kind == OP_CSR && ctx->ops[s].host.is_complex) return false;
+    return ctx->precond == FEAST_PRECOND_AMG || ctx->n >= min_n;
 }
 
 // Build the union CSR pattern over all sparse / identity slots and the per-slot value arrays.
@@ -327,6 +345,8 @@ int build_union(feast_ctx* ctx) {
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     // pass 2: per-slot values, first on the natural union pattern, then gathered into the device layout
+    const bool amg_wanted = want_amg(ctx);
+    std::vector<std::vector<double>> nat_vals(amg_wanted ? ctx->nslots : 0);
     for (int s = 0; s < ctx->nslots; ++s) {
         Operator& op = ctx->ops[s];
         std::vector<double> rv, rv2;
@@ -363,11 +383,23 @@ int build_union(feast_ctx* ctx) {
             FEAST_TRY(dev_alloc(ctx, &op.uvals_r, unnz));
             CUDA_TRY(ctx, cudaMemcpyAsync(op.uvals_r, rv2.data(), sizeof(double) * unnz, cudaMemcpyHostToDevice, ctx->stream));
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            if (amg_wanted) nat_vals[s].swap(rv);
         }
         // host copies are kept so that feast_set_problem can be called again (e.g. switching the
         // problem kind); an identity slot keeps its kind and additionally lives on the union pattern
     }
     FEAST_TRY(dev_alloc(ctx, &ctx->zvals, unnz));
+    ctx->amg_why.clear();
+    if (amg_wanted) {   // multigrid hierarchy of the Krylov preconditioner (amg_setup.cpp / amg.cu)
+        std::vector<int> dpos0(n, 0);
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t e = rowptr_f[i]; e < rowptr_f[i + 1]; ++e)
+                if (col_f[e] == (int)i) dpos0[i] = (int)e;
+        const double* vp[FEAST_MAX_SLOTS];
+        for (int s = 0; s < ctx->nslots; ++s) vp[s] = nat_vals[s].data();
+        FEAST_TRY(amg_build(ctx, n, rowptr.data(), col.data(), ctx->nslots, vp, reorder ? plan.order : std::vector<int>(), dpos0,
+                            &ctx->amg_why));
+    }
     return 0;
 }
 
@@ -380,6 +412,19 @@ int effective_solver(const feast_ctx* ctx) {
     if (!ctx->all_symmetric && ctx->bandwidth > 0 && ctx->bandwidth <= 2048) return FEAST_SOLVER_BANDED_LU;
     return FEAST_SOLVER_KRYLOV;
 }
+// the device layout (row order, tile plan, multigrid hierarchy) follows the solver settings: rebuild it from the host
+// copies of the operators; the subspace blocks are dropped
+int rebuild_layout(feast_ctx* ctx) {
+    FEAST_TRY(bind_device(ctx));
+    const int nslots = ctx->nslots;
+    free_problem_derived(ctx);
+    if (ctx->m0 != 0) free_blocks(ctx);
+    ctx->nslots = nslots;
+    FEAST_TRY(build_union(ctx));
+    ctx->problem_ready = true;
+    return 0;
+}
+
 int effective_krylov(const feast_ctx* ctx) {
     if (ctx->krylov != FEAST_KRYLOV_AUTO) return ctx->krylov;
     return ctx->all_symmetric ? FEAST_KRYLOV_COCG : FEAST_KRYLOV_GMRES;
@@ -411,6 +456,8 @@ void node_coefs(const feast_ctx* ctx, hc128 z, hc128* coef) {
     if (ctx->problem == FEAST_PROBLEM_POLYNOMIAL) {
         hc128 p(1, 0);
         for (int s = 0; s < ctx->nslots; ++s) { coef[s] = p; p *= z; }
+    } else if (ctx->problem == FEAST_PROBLEM_SAMPLED) {   // slot 0 IS T(z_k), evaluated by the caller
+        coef[0] = hc128(1, 0);
     } else {  // A - z B   (src/feast.jl:64,141)
         coef[0] = hc128(1, 0);
         coef[1] = -z;
@@ -435,6 +482,11 @@ int ensure_krylov_work(feast_ctx* ctx, int method) {
     FEAST_TRY(ensure_block(ctx, ctx->kr));
     FEAST_TRY(ensure_block(ctx, ctx->kp));
     FEAST_TRY(ensure_block(ctx, ctx->kq));
+    if (ctx->amg && method == FEAST_KRYLOV_COCG) {   // preconditioned COCG: z and the cycle's scratch, coarse-level blocks
+        FEAST_TRY(ensure_block(ctx, ctx->ks));
+        FEAST_TRY(ensure_block(ctx, ctx->kt));
+        FEAST_TRY(amg_ensure_blocks(ctx));
+    }
     if (method == FEAST_KRYLOV_BICGSTAB) {
         FEAST_TRY(ensure_block(ctx, ctx->krh));
         FEAST_TRY(ensure_block(ctx, ctx->kv));
@@ -561,7 +613,15 @@ int apply_slot_adjoint(feast_ctx* ctx, int slot, const c128* V, c128* W) {
 }
 
 // Krylov inner solve; COCG with complex64 block storage when mixed precision was requested and is applicable
-int krylov_any(feast_ctx* ctx, int method, const c128* zvals, const c128* rhs, c128* Y, KrylovResult* kr) {
+int krylov_any(feast_ctx* ctx, int method, const hc128* coef, const c128* zvals, const c128* rhs, c128* Y, KrylovResult* kr,
+               feast_stats* st) {
+    if (ctx->amg && method == FEAST_KRYLOV_COCG && !ctx->mixed_prec) {
+        int info = 0;
+        FEAST_TRY(amg_assemble(ctx, coef, zvals, &info));
+        if (info) return feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d of the coarsest multigrid operator", info);
+        if (st) amg_info(ctx, &st->precond_levels, nullptr, 0, nullptr);
+        return krylov_solve_pcocg(ctx, zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, kr);
+    }
     if (ctx->mixed_prec && method == FEAST_KRYLOV_COCG && (ctx->m0 % 2) == 0 && ctx->m0 <= 128 && ctx->tiles_ok && ctx->tile_cfg == 0)
         return krylov_solve_mixed(ctx, zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, kr);
     return krylov_solve(ctx, method, zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, kr);
@@ -632,10 +692,10 @@ int solve_shifted(feast_ctx* ctx, int solver, int method, int k, const hc128* co
                 return feast_fail(ctx, FEAST_ERR_STATE, "adjoint Krylov solve needs symmetric operators: pass them dense");
             FEAST_TRY(ensure_block(ctx, ctx->W2));
             FEAST_TRY(launch_conj(ctx, n * m, rhs, ctx->W2.p));
-            FEAST_TRY(krylov_any(ctx, method, ctx->zvals, ctx->W2.p, Y, &kr));
+            FEAST_TRY(krylov_any(ctx, method, coef, ctx->zvals, ctx->W2.p, Y, &kr, &st));   // same Z, conjugated data
             FEAST_TRY(launch_conj(ctx, n * m, Y, Y));
         } else {
-            FEAST_TRY(krylov_any(ctx, method, ctx->zvals, rhs, Y, &kr));
+            FEAST_TRY(krylov_any(ctx, method, coef, ctx->zvals, rhs, Y, &kr, &st));
         }
         st.inner_iters_total += kr.iters;
         st.inner_iters_max = std::max(st.inner_iters_max, kr.iters);
@@ -778,11 +838,12 @@ int feast_set_identity(feast_ctx* ctx, int slot, int64_t n) {
 
 int feast_set_problem(feast_ctx* ctx, int kind, int nslots) {
     ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
-    ARG_CHECK(ctx, kind >= FEAST_PROBLEM_STANDARD && kind <= FEAST_PROBLEM_POLYNOMIAL, 2, "unknown problem kind");
+    ARG_CHECK(ctx, kind >= FEAST_PROBLEM_STANDARD && kind <= FEAST_PROBLEM_SAMPLED, 2, "unknown problem kind");
     ARG_CHECK(ctx, nslots >= 1 && nslots <= FEAST_MAX_SLOTS, 3, "nslots out of range");
     if (kind == FEAST_PROBLEM_STANDARD) ARG_CHECK(ctx, nslots == 1, 3, "standard problem has one operator");
     if (kind == FEAST_PROBLEM_GENERALIZED) ARG_CHECK(ctx, nslots == 2, 3, "generalized problem has two operators");
     if (kind == FEAST_PROBLEM_POLYNOMIAL) ARG_CHECK(ctx, nslots >= 2, 3, "polynomial problem needs degree >= 1");
+    if (kind == FEAST_PROBLEM_SAMPLED) ARG_CHECK(ctx, nslots == 1, 3, "a sampled problem has one operator slot (the current sample)");
     FEAST_TRY(bind_device(ctx));
     free_problem_derived(ctx);
     if (ctx->ops[0].kind == OP_NONE) return feast_fail(ctx, FEAST_ERR_STATE, "slot 0 (A) is not set");
@@ -808,6 +869,51 @@ int feast_set_problem(feast_ctx* ctx, int kind, int nslots) {
     if (!any_dense) FEAST_TRY(build_union(ctx));
     ctx->problem_ready = true;
     return 0;
+}
+
+// Replace the sample held in slot 0 of a sampled problem (same dimension and storage class).  Subspace blocks, contour
+// and stored factorisations are kept; for sparse samples the union pattern is rebuilt (natural row order).
+int feast_set_sample_dense(feast_ctx* ctx, int64_t n, const void* a, int64_t lda, int is_complex) {
+    FEAST_TRY(check_ready(ctx, false));
+    if (ctx->problem != FEAST_PROBLEM_SAMPLED || !ctx->storage_dense)
+        return feast_fail(ctx, FEAST_ERR_STATE, "feast_set_sample_dense needs a sampled problem with dense storage");
+    ARG_CHECK(ctx, n == ctx->n, 2, "dimension differs from the problem");
+    ARG_CHECK(ctx, a != nullptr, 3, "null matrix");
+    ARG_CHECK(ctx, lda >= n, 4, "lda < n");
+    Operator& op = ctx->ops[0];
+    c128* cm = nullptr;
+    FEAST_TRY(dev_alloc(ctx, &cm, (size_t)n * n));
+    int rc = 0;
+    cudaError_t e;
+    if (is_complex) {
+        e = cudaMemcpy2DAsync(cm, sizeof(c128) * n, a, sizeof(c128) * lda, sizeof(c128) * n, n, cudaMemcpyHostToDevice, ctx->stream);
+    } else {
+        double* tmp = (double*)op.dense;
+        e = cudaMemcpy2DAsync(tmp, sizeof(double) * n, a, sizeof(double) * lda, sizeof(double) * n, n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) rc = launch_real_to_complex(ctx, n * n, tmp, cm);
+    }
+    if (e == cudaSuccess && !rc) rc = launch_colmajor_to_rowmajor(ctx, n, (int)n, cm, n, op.dense);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(cm);
+    if (e != cudaSuccess) return feast_fail(ctx, FEAST_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+int feast_set_sample_csc(feast_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval, const void* nzval,
+                         int is_complex, int index_base) {
+    FEAST_TRY(check_ready(ctx, false));
+    if (ctx->problem != FEAST_PROBLEM_SAMPLED || ctx->storage_dense)
+        return feast_fail(ctx, FEAST_ERR_STATE, "feast_set_sample_csc needs a sampled problem with sparse storage");
+    ARG_CHECK(ctx, n == ctx->n, 2, "dimension differs from the problem");
+    ARG_CHECK(ctx, colptr != nullptr, 3, "null colptr");
+    ARG_CHECK(ctx, rowval != nullptr || colptr[n] == index_base, 4, "null rowval");
+    ARG_CHECK(ctx, nzval != nullptr || colptr[n] == index_base, 5, "null nzval");
+    ARG_CHECK(ctx, index_base == 0 || index_base == 1, 7, "index_base must be 0 or 1");
+    Operator& op = ctx->ops[0];
+    FEAST_TRY(csc_to_host_csr(ctx, n, colptr, rowval, nzval, is_complex, index_base, op.host));
+    op.is_complex = is_complex != 0;
+    free_pattern(ctx);
+    return build_union(ctx);
 }
 
 // ------------------------------------------------------------------------- contour / solver / comm
@@ -838,16 +944,22 @@ int feast_set_solver(feast_ctx* ctx, int kind, int krylov, double inner_tol, int
     ctx->solver = kind; ctx->krylov = krylov; ctx->inner_tol = inner_tol; ctx->max_inner = max_inner; ctx->store = store;
     // the internal row ordering follows the solver kind (Krylov: tiled; direct: natural).  A change after
     // feast_set_problem rebuilds the device operators from the host copies and drops the subspace blocks.
-    if (ctx->problem_ready && !ctx->storage_dense && want_reorder(ctx) != ctx->reordered) {
-        FEAST_TRY(bind_device(ctx));
-        const int nslots = ctx->nslots;
-        free_problem_derived(ctx);
-        if (ctx->m0 != 0) free_blocks(ctx);
-        ctx->nslots = nslots;
-        FEAST_TRY(build_union(ctx));
-        ctx->problem_ready = true;
-    }
+    if (ctx->problem_ready && !ctx->storage_dense && (want_reorder(ctx) != ctx->reordered || want_amg(ctx) != (ctx->amg != nullptr)))
+        FEAST_TRY(rebuild_layout(ctx));
     return 0;
+}
+
+int feast_set_preconditioner(feast_ctx* ctx, int kind) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, kind >= FEAST_PRECOND_NONE && kind <= FEAST_PRECOND_AUTO, 2, "unknown preconditioner kind");
+    ctx->precond = kind;
+    if (ctx->problem_ready && !ctx->storage_dense && want_amg(ctx) != (ctx->amg != nullptr)) FEAST_TRY(rebuild_layout(ctx));
+    return 0;
+}
+
+int feast_preconditioner_info(const feast_ctx* ctx, int* nlevels, int* sizes, int cap, double* setup_seconds) {
+    if (!ctx) return feast_fail(nullptr, -1, "argument 1 invalid: null context");
+    return amg_info(ctx, nlevels, sizes, cap, setup_seconds);
 }
 
 int feast_set_mixed_precision(feast_ctx* ctx, int on) {
@@ -959,7 +1071,7 @@ int feast_get_R(feast_ctx* ctx, feast_c128* R, int64_t ldr) {
 int feast_project(feast_ctx* ctx, feast_c128* Aq, feast_c128* Bq) {
     FEAST_TRY(check_ready(ctx, true));
     ARG_CHECK(ctx, Aq != nullptr, 2, "null Aq");
-    if (ctx->problem == FEAST_PROBLEM_POLYNOMIAL)
+    if (ctx->problem == FEAST_PROBLEM_POLYNOMIAL || ctx->problem == FEAST_PROBLEM_SAMPLED)
         return feast_fail(ctx, FEAST_ERR_STATE, "feast_project applies to linear problems; use feast_beyn_reduce");
     if (ctx->problem == FEAST_PROBLEM_GENERALIZED) ARG_CHECK(ctx, Bq != nullptr, 3, "null Bq");
     const int64_t n = ctx->n;
@@ -1007,7 +1119,11 @@ int feast_recover_residual(feast_ctx* ctx, const feast_c128* Xq, const feast_c12
     FEAST_TRY(launch_colnormalize(ctx, n, m, ctx->X.p, nrm_d));            // x_j /= ||x_j||      utils.jl:113
     debug_check_finite(ctx, ctx->X.p, 2 * n * m, "recover: X normalised");
     double* hres = (double*)ctx->pinned;
-    if (ctx->problem != FEAST_PROBLEM_POLYNOMIAL) {
+    if (ctx->problem == FEAST_PROBLEM_SAMPLED) {
+        // the caller evaluates T(l_j) and finishes column by column with feast_sampled_residual
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int j = 0; j < m; ++j) res[j] = 0.0;
+    } else if (ctx->problem != FEAST_PROBLEM_POLYNOMIAL) {
         FEAST_TRY(apply_slot(ctx, 0, ctx->X.p, ctx->R.p));                 // R = A X
         const c128* BX = ctx->X.p;
         // after build_union an identity B is an OP_CSR slot with unit diagonal: skip the SpMM
@@ -1057,73 +1173,93 @@ int feast_recover_residual(feast_ctx* ctx, const feast_c128* Xq, const feast_c12
     return 0;
 }
 
-int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass, feast_stats* stats) {
-    FEAST_TRY(check_ready(ctx, true));
+// ---- the contour loop (src/feast.jl:57-71, src/nlfeast.jl:36-61) in three pieces: begin (zero the accumulators,
+// re-shard the nodes), one node (shifted solve + weighted accumulation), end (all-reduce).  feast_contour_apply runs
+// all of it in one call; the sampled-operator entries (opaque T(z) closures evaluated by the caller) drive the pieces.
+static int contour_prepare(feast_ctx* ctx, const feast_c128* lambda, int first_pass, int* solver, int* method) {
     ARG_CHECK(ctx, lambda != nullptr || first_pass, 2, "null lambda");
     if (ctx->znodes.empty()) return feast_fail(ctx, FEAST_ERR_STATE, "feast_set_contour has not been called");
-    if (first_pass && ctx->problem != FEAST_PROBLEM_POLYNOMIAL)
-        return feast_fail(ctx, -3, "argument 3 invalid: first_pass applies to polynomial problems only");
-    const int64_t n = ctx->n;
-    const int m = ctx->m0;
-    const bool poly = ctx->problem == FEAST_PROBLEM_POLYNOMIAL;
-    const int solver = effective_solver(ctx);
-    const int method = effective_krylov(ctx);
-    if (solver == FEAST_SOLVER_KRYLOV && ctx->storage_dense)
+    const bool nep = ctx->problem == FEAST_PROBLEM_POLYNOMIAL || ctx->problem == FEAST_PROBLEM_SAMPLED;
+    if (first_pass && !nep)
+        return feast_fail(ctx, -3, "argument 3 invalid: first_pass applies to nonlinear (polynomial / sampled) problems only");
+    *solver = effective_solver(ctx);
+    *method = effective_krylov(ctx);
+    if (*solver == FEAST_SOLVER_KRYLOV && ctx->storage_dense)
         return feast_fail(ctx, FEAST_ERR_STATE, "Krylov inner solves need sparse operators");
     FEAST_TRY(ensure_block(ctx, ctx->W1));
-    if (poly) FEAST_TRY(ensure_block(ctx, ctx->Q1));
-    if (solver == FEAST_SOLVER_KRYLOV) FEAST_TRY(ensure_krylov_work(ctx, method));
-    feast_stats st;
-    memset(&st, 0, sizeof(st));
-    cudaEvent_t e0 = ctx->evn[0], e1 = ctx->evn[1], e2 = ctx->evn[2], e3 = ctx->evn[3];   // owned by the context
-    PhaseTimer tm(ctx, 2);
-    int rc_final = 0;
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->Q.p, 0, sizeof(c128) * n * m, ctx->stream));           // feast.jl:58
-    if (poly) CUDA_TRY(ctx, cudaMemsetAsync(ctx->Q1.p, 0, sizeof(c128) * n * m, ctx->stream)); // nlfeast.jl:32-33
+    if (nep) FEAST_TRY(ensure_block(ctx, ctx->Q1));
+    if (*solver == FEAST_SOLVER_KRYLOV) FEAST_TRY(ensure_krylov_work(ctx, *method));
     const int nnodes = (int)ctx->znodes.size();
     if (ctx->store && (int)ctx->stored.size() != nnodes) ctx->stored.resize(nnodes);
+    return 0;
+}
+
+static bool contour_can_move_nodes(const feast_ctx* ctx, int solver) {   // stored factors / caller-evaluated samples pin nodes to ranks
+    return ctx->nranks > 1 && ctx->auto_balance && ctx->problem != FEAST_PROBLEM_SAMPLED && !(solver != FEAST_SOLVER_KRYLOV && ctx->store);
+}
+
+static int contour_begin(feast_ctx* ctx, int solver) {
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    const bool nep = ctx->problem == FEAST_PROBLEM_POLYNOMIAL || ctx->problem == FEAST_PROBLEM_SAMPLED;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->Q.p, 0, sizeof(c128) * n * m, ctx->stream));           // feast.jl:58
+    if (nep) CUDA_TRY(ctx, cudaMemsetAsync(ctx->Q1.p, 0, sizeof(c128) * n * m, ctx->stream));  // nlfeast.jl:32-33
+    if (contour_can_move_nodes(ctx, solver) && ctx->have_costs) rebalance_nodes(ctx);
+    ctx->cost_local.assign(ctx->znodes.size(), 0.0);
+    return 0;
+}
+
+static int contour_node(feast_ctx* ctx, int k, const feast_c128* lambda, int first_pass, int solver, int method, feast_stats& st,
+                        int* rc_final) {
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    const bool nep = ctx->problem == FEAST_PROBLEM_POLYNOMIAL || ctx->problem == FEAST_PROBLEM_SAMPLED;
+    cudaEvent_t e0 = ctx->evn[0], e1 = ctx->evn[1], e2 = ctx->evn[2];
     c128* d_d = ctx->vec_d();
     std::vector<hc128> d(m);
     hc128 coef[FEAST_MAX_SLOTS];
     const c128* rhs = first_pass ? ctx->X.p : ctx->R.p;
-    const bool can_move_nodes = ctx->nranks > 1 && ctx->auto_balance && !(solver != FEAST_SOLVER_KRYLOV && ctx->store);  // stored factors pin nodes to ranks
-    if (can_move_nodes && ctx->have_costs) rebalance_nodes(ctx);
-    std::vector<double> cost_local(nnodes, 0.0);
-    for (int k = 0; k < nnodes; ++k) {
-        if (ctx->owner[k] != ctx->rank) continue;
-        st.nodes_local++;
-        const hc128 z = ctx->znodes[k], w = ctx->zweights[k];
-        node_coefs(ctx, z, coef);
-        for (int j = 0; j < m; ++j)
-            d[j] = first_pass ? w : w / (z - hc128(lambda[j].re, lambda[j].im));              // feast.jl:60,69
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_d, d.data(), sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
-        cudaEventRecord(e0, ctx->stream);
-        FEAST_TRY(solve_shifted(ctx, solver, method, k, coef, rhs, ctx->W1.p, st, e1, &rc_final));
-        debug_check_finite(ctx, rhs, 2 * n * m, "contour: rhs");
-        debug_check_finite(ctx, ctx->W1.p, 2 * n * m, "contour: solve result");
-        // Q += (X - Y) diag(w/(z - l))  [feast.jl:68-70] ; polynomial: Q0, Q1 [nlfeast.jl:56-58]
-        FEAST_TRY(launch_accumulate(ctx, n, m, ctx->X.p, ctx->W1.p, d_d, ctx->Q.p, poly ? ctx->Q1.p : nullptr, z,
-                                    first_pass != 0));
-        cudaEventRecord(e2, ctx->stream);
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // d (host vector) is reused next node
-        float a = 0, b = 0;
-        cudaEventElapsedTime(&a, e0, e1);
-        cudaEventElapsedTime(&b, e1, e2);
-        st.t_factor_ms += a;
-        st.t_solve_ms += b;
-        cost_local[k] = (double)a + (double)b;
-    }
+    st.nodes_local++;
+    const hc128 z = ctx->znodes[k], w = ctx->zweights[k];
+    node_coefs(ctx, z, coef);
+    for (int j = 0; j < m; ++j)
+        d[j] = first_pass ? w : w / (z - hc128(lambda[j].re, lambda[j].im));              // feast.jl:60,69
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_d, d.data(), sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
+    cudaEventRecord(e0, ctx->stream);
+    FEAST_TRY(solve_shifted(ctx, solver, method, k, coef, rhs, ctx->W1.p, st, e1, rc_final));
+    debug_check_finite(ctx, rhs, 2 * n * m, "contour: rhs");
+    debug_check_finite(ctx, ctx->W1.p, 2 * n * m, "contour: solve result");
+    // Q += (X - Y) diag(w/(z - l))  [feast.jl:68-70] ; nonlinear: Q0, Q1 [nlfeast.jl:56-58]
+    FEAST_TRY(launch_accumulate(ctx, n, m, ctx->X.p, ctx->W1.p, d_d, ctx->Q.p, nep ? ctx->Q1.p : nullptr, z, first_pass != 0));
+    cudaEventRecord(e2, ctx->stream);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // d (host vector) goes out of scope
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, e0, e1);
+    cudaEventElapsedTime(&b, e1, e2);
+    st.t_factor_ms += a;
+    st.t_solve_ms += b;
+    ctx->cost_local[k] = (double)a + (double)b;
+    return 0;
+}
+
+static int contour_end(feast_ctx* ctx, int solver, feast_stats& st) {
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    const bool nep = ctx->problem == FEAST_PROBLEM_POLYNOMIAL || ctx->problem == FEAST_PROBLEM_SAMPLED;
+    const int nnodes = (int)ctx->znodes.size();
     if (ctx->nranks > 1) {                                                                     // NC1
         const NcclApi* api = nccl_api();
+        cudaEvent_t e0 = ctx->evn[0], e3 = ctx->evn[3];
+        const bool can_move_nodes = contour_can_move_nodes(ctx, solver);
         cudaEventRecord(e0, ctx->stream);
         int rc = api->AllReduce(ctx->Q.p, ctx->Q.p, (size_t)2 * n * m, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
-        if (!rc && poly)
+        if (!rc && nep)
             rc = api->AllReduce(ctx->Q1.p, ctx->Q1.p, (size_t)2 * n * m, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
         if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclAllReduce: %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
         cudaEventRecord(e3, ctx->stream);
         if (can_move_nodes) {   // share the measured per-node costs (nnodes doubles) for the next pass
             double* cbuf = ctx->vec_cost();
-            CUDA_TRY(ctx, cudaMemcpyAsync(cbuf, cost_local.data(), sizeof(double) * nnodes, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(cbuf, ctx->cost_local.data(), sizeof(double) * nnodes, cudaMemcpyHostToDevice, ctx->stream));
             rc = api->AllReduce(cbuf, cbuf, (size_t)nnodes, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
             if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclAllReduce (node costs) failed");
             CUDA_TRY(ctx, cudaMemcpyAsync(ctx->node_cost.data(), cbuf, sizeof(double) * nnodes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1134,8 +1270,10 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
         cudaEventElapsedTime(&c, e0, e3);
         st.t_reduce_ms = c;
     }
-    st.t_total_ms = tm.stop();
-    if (stats) *stats = st;
+    return 0;
+}
+
+static int contour_finish(feast_ctx* ctx, const feast_stats& st, int rc_final) {
     if (st.info) return feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d of a shifted factorisation", st.info);
     if (rc_final == FEAST_WARN_INNER_MAXIT)
         feast_fail(ctx, FEAST_WARN_INNER_MAXIT, "inner solve did not reach inner_tol=%.1e (max_inner=%d, relres %.3e)", ctx->inner_tol,
@@ -1143,12 +1281,92 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
     return rc_final;
 }
 
+int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass, feast_stats* stats) {
+    FEAST_TRY(check_ready(ctx, true));
+    if (ctx->problem == FEAST_PROBLEM_SAMPLED)
+        return feast_fail(ctx, FEAST_ERR_STATE, "sampled operators are applied node by node: use feast_contour_node");
+    int solver = 0, method = 0;
+    FEAST_TRY(contour_prepare(ctx, lambda, first_pass, &solver, &method));
+    feast_stats st;
+    memset(&st, 0, sizeof(st));
+    PhaseTimer tm(ctx, 2);
+    int rc_final = 0;
+    FEAST_TRY(contour_begin(ctx, solver));
+    const int nnodes = (int)ctx->znodes.size();
+    for (int k = 0; k < nnodes; ++k) {
+        if (ctx->owner[k] != ctx->rank) continue;
+        FEAST_TRY(contour_node(ctx, k, lambda, first_pass, solver, method, st, &rc_final));
+    }
+    FEAST_TRY(contour_end(ctx, solver, st));
+    st.t_total_ms = tm.stop();
+    if (stats) *stats = st;
+    return contour_finish(ctx, st, rc_final);
+}
+
+// Sampled operators (the closure form nlfeast!(T::Function, ...), src/nlfeast.jl:2-4): slot 0 holds the caller's
+// evaluation of T at ONE point.  For every contour node the caller uploads T(z_k) with feast_set_sample_* and calls
+// feast_contour_node (phase bit 1: first node of the pass, bit 2: last node); with store != 0 the factorisation of a
+// node is kept, so later passes need no sample for it (feast_node_needs_sample).
+int feast_contour_node(feast_ctx* ctx, int k, const feast_c128* lambda, int first_pass, int phase, feast_stats* stats) {
+    FEAST_TRY(check_ready(ctx, true));
+    if (ctx->problem != FEAST_PROBLEM_SAMPLED)
+        return feast_fail(ctx, FEAST_ERR_STATE, "feast_contour_node applies to sampled problems (FEAST_PROBLEM_SAMPLED)");
+    int solver = 0, method = 0;
+    FEAST_TRY(contour_prepare(ctx, lambda, first_pass, &solver, &method));
+    ARG_CHECK(ctx, k >= -1 && k < (int)ctx->znodes.size(), 2, "node index out of range");
+    PhaseTimer tm(ctx, 2);
+    if (phase & 1) {
+        memset(&ctx->pass_stats, 0, sizeof(ctx->pass_stats));
+        ctx->pass_rc = 0;
+        FEAST_TRY(contour_begin(ctx, solver));
+    }
+    if (k >= 0) FEAST_TRY(contour_node(ctx, k, lambda, first_pass, solver, method, ctx->pass_stats, &ctx->pass_rc));   // k = -1: no local node
+    if (phase & 2) FEAST_TRY(contour_end(ctx, solver, ctx->pass_stats));
+    ctx->pass_stats.t_total_ms += tm.stop();
+    if (stats) *stats = ctx->pass_stats;
+    return (phase & 2) ? contour_finish(ctx, ctx->pass_stats, ctx->pass_rc) : 0;
+}
+
+int feast_node_needs_sample(const feast_ctx* ctx, int k) {
+    if (!ctx || k < 0 || k >= (int)ctx->znodes.size()) return -1;
+    if (!ctx->store) return 1;
+    if (k < (int)ctx->stored.size() && ctx->stored[k].lu) return 0;
+    if (k < (int)ctx->bstored.size() && ctx->bstored[k].lu) return 0;
+    return 1;
+}
+
+// Column j of the nonlinear residual with the current sample T(l_j) in slot 0 (src/utils.jl:104-109,151-157):
+// R[:, j] = T x_j ; res = ||R_j|| / fro  (fro = ||T(l_j)||_F, computed by the caller who holds the matrix).
+int feast_sampled_residual(feast_ctx* ctx, int j, double fro, double* res) {
+    FEAST_TRY(check_ready(ctx, true));
+    if (ctx->problem != FEAST_PROBLEM_SAMPLED) return feast_fail(ctx, FEAST_ERR_STATE, "sampled problems only");
+    ARG_CHECK(ctx, j >= 0 && j < ctx->m0, 2, "column out of range");
+    ARG_CHECK(ctx, fro > 0.0, 3, "norm must be positive");
+    ARG_CHECK(ctx, res != nullptr, 4, "null output");
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    const Operator& op = ctx->ops[0];
+    PhaseTimer tm(ctx, 1);
+    if (op.kind == OP_DENSE)
+        FEAST_TRY(launch_zgemm(ctx, (int)n, 1, n, hc128(1, 0), op.dense, n, 1, false, ctx->X.p + j, m, 1, hc128(0, 0), ctx->R.p + j, m, 1));
+    else
+        FEAST_TRY(launch_spmm(ctx, n, 1, ctx->u_rowptr, ctx->u_col, op.uvals_r, op.uvals_c, ctx->X.p + j, m, ctx->R.p + j, m, nullptr));
+    double* nrm_d = ctx->vec_nrm();
+    FEAST_TRY(launch_colnorm2(ctx, n, m, ctx->R.p, nrm_d));
+    double* h = (double*)ctx->pinned;
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, nrm_d + j, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *res = std::sqrt(h[0]) / fro;
+    tm.stop();
+    return 0;
+}
+
 // Stochastic eigenvalue-count estimate (src/stochastic.jl:2-33): the current subspace block X holds the
 // probe vectors; est = Re sum_k w_k tr(X' (z_k B - A)^-1 X) / m0, node-sharded like the contour loop.
 int feast_estimate_count(feast_ctx* ctx, double* est, feast_stats* stats) {
     FEAST_TRY(check_ready(ctx, true));
     ARG_CHECK(ctx, est != nullptr, 2, "null output");
-    if (ctx->problem == FEAST_PROBLEM_POLYNOMIAL)
+    if (ctx->problem == FEAST_PROBLEM_POLYNOMIAL || ctx->problem == FEAST_PROBLEM_SAMPLED)
         return feast_fail(ctx, FEAST_ERR_STATE, "feast_estimate_count applies to linear problems");
     if (ctx->znodes.empty()) return feast_fail(ctx, FEAST_ERR_STATE, "feast_set_contour has not been called");
     const int64_t n = ctx->n;
@@ -1219,7 +1437,8 @@ int feast_dual_project(feast_ctx* ctx, feast_c128* G) {
     FEAST_TRY(check_ready(ctx, true));
     ARG_CHECK(ctx, G != nullptr, 2, "null G");
     if (!ctx->Ql.p) return feast_fail(ctx, FEAST_ERR_STATE, "feast_dual_set_subspace has not been called");
-    if (ctx->problem == FEAST_PROBLEM_POLYNOMIAL) return feast_fail(ctx, FEAST_ERR_STATE, "linear problems only");
+    if (ctx->problem == FEAST_PROBLEM_POLYNOMIAL || ctx->problem == FEAST_PROBLEM_SAMPLED)
+        return feast_fail(ctx, FEAST_ERR_STATE, "linear problems only");
     const int m = ctx->m0;
     PhaseTimer tm(ctx, 0);
     FEAST_TRY(ensure_block(ctx, ctx->W1));
@@ -1407,6 +1626,7 @@ int feast_factorize(feast_ctx* ctx, const feast_c128* coef, int ncoef, feast_fac
     for (int s = 0; s < FEAST_MAX_SLOTS; ++s) cf[s] = s < ncoef ? hc128(coef[s].re, coef[s].im) : hc128(0, 0);
     feast_factor* F = new feast_factor();
     F->kind = effective_solver(ctx);
+    for (int s = 0; s < FEAST_MAX_SLOTS; ++s) F->coef[s] = cf[s];
     if (F->kind == FEAST_SOLVER_DENSE_LU) {
         if (!ctx->red_d) {  // getrf scratch when no subspace has been set yet
             FEAST_TRY(dev_alloc(ctx, &ctx->red_d, ((size_t)1 << 20) / sizeof(double)));
@@ -1479,7 +1699,7 @@ int feast_solve(feast_ctx* ctx, const feast_factor* F, int64_t n, int nrhs, cons
             // Z symmetric: Z^H = conj(Z)  ->  Z^H y = b  <=>  Z conj(y) = conj(b)
             return feast_fail(ctx, FEAST_ERR_STATE, "adjoint Krylov solve is not implemented yet");
         }
-        FEAST_TRY(krylov_solve(ctx, method, F->zvals, rhs, ctx->W1.p, ctx->inner_tol, ctx->max_inner, &kr));
+        FEAST_TRY(krylov_any(ctx, method, F->coef, F->zvals, rhs, ctx->W1.p, &kr, nullptr));
         if (!kr.converged) rc_final = FEAST_WARN_INNER_MAXIT;
     }
     FEAST_TRY(launch_rowmajor_to_colmajor(ctx, n, m, ctx->W1.p, ctx->stage, n, ctx->perm_d));

@@ -98,9 +98,11 @@ struct feast_factor {        // fine-grained plugin handle
     c128* zvals = nullptr;   // Krylov / banded: assembled union-pattern values
     BandFactor band;
     bool symmetric = false;
+    hc128 coef[FEAST_MAX_SLOTS];   // the shift coefficients (the multigrid levels are assembled from them at solve time)
 };
 
 struct NcclApi;              // nccl_dl.cpp
+struct AmgDev;               // amg.cu
 
 struct feast_ctx {
     int device = 0;
@@ -142,12 +144,18 @@ struct feast_ctx {
     std::vector<int> owner;       // node -> rank
     std::vector<double> node_cost; // measured device ms of the last solve of each node (all ranks, after the all-reduce)
     bool have_costs = false;
+    std::vector<double> cost_local;   // this rank's measurements of the running pass
+    feast_stats pass_stats;       // statistics of the running pass (node-by-node entries)
+    int pass_rc = 0;
     int auto_balance = 1;         // re-shard nodes by measured cost before every contour pass (Krylov / store=0 only)
     // solver
     int solver = FEAST_SOLVER_AUTO, krylov = FEAST_KRYLOV_AUTO;
     double inner_tol = 1e-10;
     int max_inner = 5000;
     int store = 0;
+    int precond = FEAST_PRECOND_AUTO;   // Krylov preconditioner request (feast_set_preconditioner)
+    AmgDev* amg = nullptr;        // smoothed-aggregation hierarchy (built with the union pattern when applicable)
+    std::string amg_why;          // why no hierarchy was built (diagnostic)
     int mixed_prec = 0;           // EXPERIMENTAL: complex64 storage of the COCG blocks (feast_set_mixed_precision)
     std::vector<DenseLU> stored;  // per node (only local nodes populated)
     std::vector<BandFactor> bstored; // per node, banded solver

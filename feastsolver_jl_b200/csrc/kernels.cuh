@@ -71,8 +71,19 @@ int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs,
 
 // EXPERIMENTAL: COCG with complex64 storage of the Krylov blocks (mixed_prec); needs m0 even and the default tile plan
 int krylov_solve_mixed(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out);
+// COCG preconditioned by the smoothed-aggregation V-cycle (needs ctx->amg assembled for the node)
+int krylov_solve_pcocg(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out);
 int gmres_solve(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out);
 size_t gmres_small_bytes(int m, int R);
+
+// ---- amg.cu: smoothed-aggregation preconditioner of the Krylov inner solves
+int amg_build(feast_ctx* ctx, int64_t n, const int64_t* rowptr, const int* col, int nslots, const double* const* vals,
+              const std::vector<int>& order, const std::vector<int>& dpos0, std::string* why);
+void amg_free(feast_ctx* ctx);
+int amg_ensure_blocks(feast_ctx* ctx);
+int amg_assemble(feast_ctx* ctx, const hc128* coef, const c128* zvals0, int* info);
+int amg_apply(feast_ctx* ctx, const c128* zvals0, const c128* r, c128* y, c128* t);
+int amg_info(const feast_ctx* ctx, int* nlevels, int* sizes, int cap, double* setup_seconds);
 
 // ---- dense.cu ------------------------------------------------------------------
 // In-place LU with partial pivoting of ROW-major n x n Z (Z(i,j) = Z[i*n + j]); ipiv device 0-based.

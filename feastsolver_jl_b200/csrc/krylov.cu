@@ -154,6 +154,52 @@ __global__ void cocg_p_kernel(int64_t total, int m, c128* __restrict__ x, c128* 
     }
 }
 
+// ----------------------------------------------------------------------------- preconditioned COCG pieces
+// after r -= alpha q: reduce the ||r||^2 partials (third entry of each triple), convergence bookkeeping; beta comes later
+__global__ void __launch_bounds__(1024) pcocg_check_kernel(int m, int nblocks, const double* __restrict__ partials, KryScal s, double tol2) {
+    extern __shared__ double red[];  // [m]
+    __shared__ int cnt;
+    __shared__ double rmax;
+    if (threadIdx.x == 0) { cnt = 0; rmax = 0.0; }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = warp; j < m; j += nw) {
+        double v = 0.0;
+        for (int b = lane; b < nblocks; b += 32) v += partials[(int64_t)b * 3 * m + 3 * j + 2];
+        for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[j] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const double nn = red[j];
+        s.rn2[j] = nn;
+        if (s.active[j] && (nn <= tol2 * s.bn2[j] || !isfinite(nn))) s.active[j] = 0;
+        if (s.active[j]) atomicAdd(&cnt, 1);
+        const double rel = s.bn2[j] > 0.0 ? sqrt(nn / s.bn2[j]) : 0.0;
+        unsigned long long* addr = (unsigned long long*)&rmax;
+        unsigned long long old = *addr, assumed;
+        do {
+            assumed = old;
+            if (__longlong_as_double((long long)assumed) >= rel) break;
+            old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(rel));
+        } while (assumed != old);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { *s.nactive = cnt; *s.relmax = rmax; }
+}
+// beta = <r, z>_new / rho ; rho = <r, z>_new   [new value in tmp1]
+__global__ void pcocg_beta_kernel(int m, KryScal s) {
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        c128 b = cmake(0.0, 0.0);
+        if (s.active[j]) {
+            const c128 rn = s.tmp1[j], ro = s.rho[j];
+            if (cabs2(ro) > 0.0 && isfinite(rn.x) && isfinite(rn.y)) b = cdiv(rn, ro);
+            else s.active[j] = 0;
+            s.rho[j] = rn;
+        }
+        s.beta[j] = b;
+    }
+}
+
 // ----------------------------------------------------------------------------- BiCGStab pieces
 // beta = (rho'/rho)(alpha/omega); rho = rho'   [rho' in tmp1]
 __global__ void bicg_beta_kernel(int m, KryScal s) {
@@ -393,6 +439,84 @@ int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs,
                 if (hf->nactive == 0) break;
             }
         }
+    }
+    if (out) {
+        out->iters = iters;
+        out->relres_max = hf->relmax;
+        out->converged = (hf->relmax <= tol * (1.0 + 1e-12));
+        out->spmm_ms = spmm_ms;
+        out->spmm_launches = spmm_launches;
+    }
+    return 0;
+}
+
+// =============================================================================== preconditioned COCG
+// COCG with the smoothed-aggregation V-cycle (amg.cu) as a complex symmetric preconditioner M^-1:
+//     z = M^-1 r ; rho = <r, z> ; p = z + beta p ; q = Z p ; alpha = rho / <p, q> ; x += alpha p ; r -= alpha q
+// (unconjugated bilinear forms throughout).  Per iteration: one fine SpMM for q, one V-cycle (two fine SpMMs plus the
+// coarse levels) and 3 + 1 + 5 block passes of vector work; on the C2 pencil it needs ~10x fewer iterations than
+// the plain recurrence (numpy prototype of the same cycle: 262 instead of 2831 over the 8 upper nodes at 64^3).
+int krylov_solve_pcocg(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out) {
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    const int64_t total = n * m;
+    const size_t bytes = sizeof(c128) * total;
+    KryScal s = carve_scalars(ctx);
+    const double tol2 = tol * tol;
+    c128 *x = Y, *r = ctx->kr.p, *p = ctx->kp.p, *q = ctx->kq.p, *z = ctx->ks.p, *t = ctx->kt.p;
+    cudaStream_t st = ctx->stream;
+    struct HostFlag { int nactive; int pad; double relmax; };
+    HostFlag* hf = (HostFlag*)ctx->pinned;
+    const int check_every = 4;
+    cudaEvent_t* evs = ctx->evk;
+    int ev_n = 0, spmm_launches = 0, iters = 0;
+    double spmm_ms = 0.0;
+    auto ev_flush = [&]() {
+        for (int i = 0; i < ev_n; ++i) { float tt = 0; cudaEventElapsedTime(&tt, evs[2 * i], evs[2 * i + 1]); spmm_ms += tt; }
+        spmm_launches += ev_n;
+        ev_n = 0;
+    };
+    CUDA_TRY(ctx, cudaMemsetAsync(x, 0, bytes, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(r, Rhs, bytes, cudaMemcpyDeviceToDevice, st));
+    FEAST_TRY(launch_colnorm2(ctx, n, m, r, s.bn2));
+    FEAST_TRY(amg_apply(ctx, zvals, r, z, t));
+    CUDA_TRY(ctx, cudaMemcpyAsync(p, z, bytes, cudaMemcpyDeviceToDevice, st));
+    FEAST_TRY(launch_coldot(ctx, n, m, r, z, false, s.rho));
+    kry_init_scalars<<<1, 128, 0, st>>>(m, s, tol2);
+    KLAUNCH_CHECK(ctx);
+    const int rgrid = red_grid_k(n, m);
+    hf->nactive = -1;
+    hf->relmax = 1.0;
+    while (iters < maxit) {
+        cudaEventRecord(evs[2 * ev_n], st);
+        FEAST_TRY(launch_spmm(ctx, n, m, ctx->u_rowptr, ctx->u_col, nullptr, zvals, p, m, q, m, s.mu));   // q = Z p, mu = <p, q>
+        cudaEventRecord(evs[2 * ev_n + 1], st);
+        ++ev_n;
+        cocg_alpha_kernel<<<1, 128, 0, st>>>(m, s);
+        KLAUNCH_CHECK(ctx);
+        cocg_update_kernel<<<rgrid, 256, 768 * sizeof(double), st>>>(n, m, r, q, s, ctx->red_d);
+        KLAUNCH_CHECK(ctx);
+        pcocg_check_kernel<<<1, 1024, m * sizeof(double), st>>>(m, rgrid, ctx->red_d, s, tol2);
+        KLAUNCH_CHECK(ctx);
+        ++iters;
+        const bool check = (iters % check_every == 0 || iters == maxit);
+        if (check) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(&hf->nactive, s.nactive, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaMemcpyAsync(&hf->relmax, s.relmax, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            ev_flush();
+        }
+        const bool done = check && hf->nactive == 0;
+        if (!done) {                                     // the last iteration needs no new direction
+            FEAST_TRY(amg_apply(ctx, zvals, r, z, t));
+            FEAST_TRY(launch_coldot(ctx, n, m, r, z, false, s.tmp1));
+            pcocg_beta_kernel<<<1, 128, 0, st>>>(m, s);
+            KLAUNCH_CHECK(ctx);
+        }
+        // x += alpha p (columns active in this iteration) ; p = z + beta p (columns still active)
+        cocg_p_kernel<<<ew_grid_k(total), 256, 0, st>>>(total, m, x, p, z, s);
+        KLAUNCH_CHECK(ctx);
+        if (done) break;
     }
     if (out) {
         out->iters = iters;

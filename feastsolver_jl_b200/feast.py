@@ -106,8 +106,20 @@ class FeastContext:
         w = np.ascontiguousarray(weights, dtype=np.complex128)
         self._ck(self.lib.feast_set_contour(self.h, len(z), _lib.ptr(z), _lib.ptr(w)))
 
-    def set_solver(self, kind=_lib.SOLVER_AUTO, krylov=_lib.KRYLOV_AUTO, inner_tol=1e-8, max_inner=4000, store=False):
+    def set_solver(self, kind=_lib.SOLVER_AUTO, krylov=_lib.KRYLOV_AUTO, inner_tol=1e-8, max_inner=4000, store=False, precond=None):
+        if precond is not None:   # before set_solver: one layout rebuild at most
+            self.set_preconditioner(precond)
         self._ck(self.lib.feast_set_solver(self.h, kind, krylov, float(inner_tol), int(max_inner), int(bool(store))))
+
+    def set_preconditioner(self, kind=_lib.PRECOND_AUTO):
+        """Krylov preconditioner: PRECOND_NONE / PRECOND_AMG (smoothed-aggregation V-cycle) / PRECOND_AUTO."""
+        self._ck(self.lib.feast_set_preconditioner(self.h, int(kind)))
+
+    def preconditioner_info(self):
+        nl, secs = C.c_int(0), C.c_double(0.0)
+        sizes = np.zeros(16, dtype=np.int32)
+        self._ck(self.lib.feast_preconditioner_info(self.h, C.byref(nl), _lib.ptr(sizes), 16, C.byref(secs)))
+        return {"levels": int(nl.value), "sizes": [int(v) for v in sizes[:nl.value]], "setup_s": float(secs.value)}
 
     def layout_info(self):
         """Internal layout of the sparse path: renumbered?, tiles, natural bandwidth, tiled SpMM in use, halo rows per row."""

@@ -63,7 +63,13 @@ enum { FEAST_SOLVER_AUTO = 0, FEAST_SOLVER_DENSE_LU = 1, FEAST_SOLVER_KRYLOV = 2
 enum { FEAST_KRYLOV_AUTO = 0, FEAST_KRYLOV_COCG = 1, FEAST_KRYLOV_BICGSTAB = 2, FEAST_KRYLOV_GMRES = 3 };
 enum { FEAST_PROBLEM_STANDARD = 0,    /* A x = l x          feast!      src/feast.jl:10-80   */
        FEAST_PROBLEM_GENERALIZED = 1, /* A x = l B x        gen_feast!  src/feast.jl:89-156  */
-       FEAST_PROBLEM_POLYNOMIAL = 2   /* sum l^i A_i x = 0  nlfeast!    src/nlfeast.jl:2-84  */ };
+       FEAST_PROBLEM_POLYNOMIAL = 2,  /* sum l^i A_i x = 0  nlfeast!    src/nlfeast.jl:2-84  */
+       FEAST_PROBLEM_SAMPLED = 3      /* T(l) x = 0 with T an opaque callable of the caller (the closure form
+                                         nlfeast!(T::Function, ...), src/nlfeast.jl:2-4): slot 0 holds T at ONE point,
+                                         re-uploaded by the caller for every node / Ritz value                       */ };
+/* Preconditioner of the Krylov inner solves: a smoothed-aggregation multigrid V-cycle built from the real symmetric
+ * operator slots (linear problems, COCG).  AUTO = use it when applicable and n is large enough to pay for the setup. */
+enum { FEAST_PRECOND_NONE = 0, FEAST_PRECOND_AMG = 1, FEAST_PRECOND_AUTO = 2 };
 #define FEAST_MAX_SLOTS 8            /* slot 0 = A (or A_0), 1 = B (or A_1), ... A_7 */
 
 typedef struct {
@@ -78,6 +84,8 @@ typedef struct {
     double t_total_ms;
     double t_spmm_ms;         /* Krylov: device time inside the SpMM launches       */
     int64_t spmm_launches;    /* Krylov: number of SpMM launches                    */
+    int    precond_levels;    /* levels of the multigrid preconditioner in use (0: unpreconditioned) */
+    int    reserved0;
 } feast_stats;
 
 /* ---- library / context ---------------------------------------------- */
@@ -149,6 +157,15 @@ FEAST_API int  feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int
  * src/utils.jl:70); returns Rf (m0 x m0) and G1 = U' Q1 (utils.jl:71).  The caller
  * finishes the m0 x m0 SVD/eig (utils.jl:72-76) and calls feast_recover_residual
  * with Xq = Ur * vecs.                                                          */
+/* sampled problems (opaque T(z)): replace the sample in slot 0, apply ONE contour node with it (phase bit 1 = first
+ * node of the pass, bit 2 = last; k = -1: this rank owns no node, collective part only), finish the residual of
+ * column j with the sample T(l_j) (fro = ||T(l_j)||_F from the caller).  src/nlfeast.jl:36-61, src/utils.jl:104-109,151-157 */
+FEAST_API int  feast_set_sample_dense(feast_ctx* ctx, int64_t n, const void* a, int64_t lda, int is_complex);
+FEAST_API int  feast_set_sample_csc(feast_ctx* ctx, int64_t n, const int64_t* colptr, const int64_t* rowval,
+                                    const void* nzval, int is_complex, int index_base);
+FEAST_API int  feast_contour_node(feast_ctx* ctx, int k, const feast_c128* lambda, int first_pass, int phase, feast_stats* stats);
+FEAST_API int  feast_node_needs_sample(const feast_ctx* ctx, int k);   /* 0 when a stored factorisation of node k exists */
+FEAST_API int  feast_sampled_residual(feast_ctx* ctx, int j, double fro, double* res);
 FEAST_API int  feast_beyn_reduce(feast_ctx* ctx, feast_c128* Rf, feast_c128* G1);
 /* contour_estimate_eig (src/stochastic.jl:2-33): with the probe vectors uploaded by
  * feast_set_subspace, est = Re sum_k w_k tr(X' (z_k B - A)^-1 X) / m0 (node-sharded).   */
@@ -200,6 +217,10 @@ FEAST_API int  feast_phase_times(feast_ctx* ctx, double* ms3, int reset);
  * Krylov path: the COCG blocks are stored in complex64 (half the HBM traffic), arithmetic stays double.
  * Applies when the inner solver is COCG, m0 is even and the default tile plan is in use; ignored otherwise. */
 FEAST_API int  feast_set_mixed_precision(feast_ctx* ctx, int on);
+/* kind: FEAST_PRECOND_*.  Takes effect immediately (the device layout is rebuilt if a hierarchy has to be added or dropped). */
+FEAST_API int  feast_set_preconditioner(feast_ctx* ctx, int kind);
+/* levels in use (0 = none), their sizes (up to cap entries) and the host setup time of the hierarchy */
+FEAST_API int  feast_preconditioner_info(const feast_ctx* ctx, int* nlevels, int* sizes, int cap, double* setup_seconds);
 /* Internal layout of the sparse path (no reference counterpart: UMFPACK reorders internally as
  * well).  The rows are cut into tiles whose referenced rows of the n x m0 block fit in shared
  * memory (tiled SpMM); with Krylov inner solves the rows are renumbered so that the tiles are
@@ -216,6 +237,13 @@ FEAST_API int  feast_debug_tile_plan(int64_t n, const int64_t* rowptr, const int
 /* Host-only restatement of the library's orthonormalisation (iterated, shifted Cholesky-QR; replaces
  * `qr(Q).Q`, src/feast.jl:41, and the tall `svd!(Q0)` of src/utils.jl:70) for CPU regression tests:
  * V (n x m column-major, ldv) is overwritten with the orthonormal factor, V_in = V_out * Rtot.     */
+/* host-only: smoothed-aggregation hierarchy of the Krylov preconditioner (amg_setup.cpp), for CPU tests of the setup */
+FEAST_API void* feast_debug_amg_build(int64_t n, const int64_t* rowptr, const int* col, int nslots, const double* vals_flat,
+                                      int max_coarse, int* nlevels, double* seconds);
+FEAST_API int  feast_debug_amg_level_info(const void* handle, int lev, int* n, int* nnz, int* nc, int* pnnz, double* rho);
+FEAST_API int  feast_debug_amg_level_get(const void* handle, int lev, int* rowptr, int* col, double* vals_flat,
+                                         int* p_rowptr, int* p_col, double* p_val);
+FEAST_API void feast_debug_amg_free(void* handle);
 FEAST_API int  feast_debug_cholqr(int64_t n, int m, feast_c128* V, int64_t ldv, feast_c128* Rtot, int* passes);
 
 #ifdef __cplusplus
