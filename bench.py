@@ -39,7 +39,8 @@ TARGET = 36
 INNER_TOL = 1e-5
 MAX_INNER = 6000
 EPS = 1e-12
-CPU_GRID = 24          # reduced grid for the CPU arm (sparse LU of the 100^3 pencil does not fit)
+SAME_GRID = 48         # largest CPU-feasible grid of the same pencil: both arms run it for the like-for-like ratio
+CPU_BUDGET_S = 240.0   # cap on the CPU work of one bench invocation (the sparse LU of the 100^3 pencil does not fit at all)
 
 
 def measured_peaks():
@@ -114,72 +115,91 @@ def spmm_bytes(n, nnz, m0):
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_sample(nsolves, grid=CPU_GRID):
-    """Oracle (numpy/scipy restatement of the reference, SuperLU in place of UMFPACK) on a bounded
-    sample: `nsolves` node solves (factor A - zB + solve m0 right-hand sides) at a reduced grid."""
-    from oracle import feast_oracle as fo
+def _blas_threads():
     try:
         from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+        return int(max([p.get("num_threads", 1) for p in threadpool_info()] + [1]))
     except Exception:
-        threads = os.cpu_count() or 1
+        return int(os.cpu_count() or 1)
+
+
+def cpu_node_solves(grid, nsolves):
+    """Oracle (numpy/scipy restatement of the reference, SuperLU in place of UMFPACK): `nsolves` contour-node solves
+    (factor A - z_k B, solve M0 right-hand sides: src/feast.jl:141-143) of the C2 pencil at `grid`^3.  Returns seconds."""
+    from oracle import feast_oracle as fo
     A, B, c, r, cnt, X0 = build_workload(grid)
     ct = fo.circular_contour_gauss(c, r, NODES)
-    R = X0
     t0 = time.perf_counter()
     for k in range(nsolves):
         F = fo.lu_factorizer(A - B * ct.nodes[k % NODES])
-        fo.left_divide(F, R)
-    dt = time.perf_counter() - t0
-    return {"value": nsolves / dt, "unit": "node_solves/s", "cores": int(threads), "kind": "port",
-            "sample": f"{nsolves} node solves (sparse LU factor + {M0}-rhs solve) of the same pencil on a "
-                      f"{grid}^3 grid (n={grid**3}); the 100^3 sparse LU does not fit host memory/time; "
-                      f"numpy/scipy restatement of the Julia reference (SuperLU for UMFPACK)",
+        fo.left_divide(F, X0)
+    return time.perf_counter() - t0
+
+
+def pick_cpu_grid(nsolves, budget_s, candidates=(48, 40, 32, 24)):
+    """Largest grid whose `nsolves` node solves fit the budget, from one timed solve at 20^3 and the n^2 growth of a
+    3-D nested-dissection LU (measured here: 12.6 s / 40.3 s per factorisation at 32^3 / 40^3, ratio 3.2 ~ (40/32)^6 = 3.8)."""
+    t20 = cpu_node_solves(20, 1)
+    for g in candidates:
+        if nsolves * t20 * (g / 20.0) ** 6 <= budget_s:
+            return g, t20
+    return candidates[-1], t20
+
+
+def cpu_sample(grid, nsolves):
+    dt = cpu_node_solves(grid, nsolves)
+    return {"value": nsolves / dt, "unit": "node_solves/s", "cores": _blas_threads(), "kind": "port", "grid": grid,
+            "sample": f"{nsolves} contour-node solve(s) (sparse LU of A - zB + {M0}-rhs solve) of the same pencil on a "
+                      f"{grid}^3 grid (n={grid**3}): the largest grid whose factorisation fits {CPU_BUDGET_S:.0f} s of host time "
+                      f"(the 100^3 sparse LU does not fit host memory/time); numpy/scipy restatement of the Julia reference "
+                      f"(SuperLU for UMFPACK)",
             "seconds": dt}
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU path (oracle port) on the host cores.  One step = ONE contour-node solve of the
+    C2 pencil at the largest grid for which steps + warmup solves fit CPU_BUDGET_S."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import feast_oracle as fo
-    A, B, c, r, cnt, X0 = build_workload(CPU_GRID)
-    ct = fo.circular_contour_gauss(c, r, NODES)
-    # one step = one outer iteration of the oracle driver (16 factor+solve node solves + RR) on the sample
     steps, warm = max(1, args.steps), max(0, min(args.warmup, 1))
-    tms = fo.Timers()
-    X = X0.copy()
-    t_all = []
-    for it in range(warm + steps):
-        t0 = time.perf_counter()
-        fo.gen_feast(X, A, B, ct, iter=1, eps=0.0, timers=tms)  # iter=1: exactly one pass with solves
-        t_all.append(time.perf_counter() - t0)
-    dt = sum(t_all[warm:])
-    val = NODES * steps / dt
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        threads = os.cpu_count() or 1
-    sample = (f"oracle gen_feast outer iterations on a {CPU_GRID}^3 grid (n={CPU_GRID**3}), m0={M0}, {NODES} nodes; "
-              f"numpy/scipy restatement of the Julia reference (SuperLU for UMFPACK); 100^3 sparse LU infeasible on host")
+    grid = args.grid if args.grid_given else pick_cpu_grid(steps + warm, CPU_BUDGET_S)[0]
+    if warm:
+        cpu_node_solves(grid, warm)
+    dt = cpu_node_solves(grid, steps)
+    val = steps / dt
+    sample = (f"{steps} contour-node solves (sparse LU + {M0}-rhs solve; one per step) on a {grid}^3 grid (n={grid**3}), "
+              f"the largest of 48/40/32/24 whose {steps + warm} solves fit {CPU_BUDGET_S:.0f} s; numpy/scipy restatement of the "
+              f"Julia reference (SuperLU for UMFPACK); the 100^3 sparse LU is infeasible on the host")
     out = {"impl": "reference", "metric": "contour_node_solves_per_sec", "value": val, "unit": "node_solves/s",
            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-           "config": {"workload": f"C2-sample: 3-D Laplacian+mass pencil grid {CPU_GRID}^3, m0={M0}, {NODES} Gauss nodes (CPU arm)"},
-           "cpu_baseline": {"value": val, "unit": "node_solves/s", "cores": int(threads), "kind": "port", "sample": sample},
+           "config": {"workload": f"C2 pencil (3-D Laplacian + mass), grid {grid}^3, m0={M0}, {NODES} Gauss nodes; CPU arm: "
+                                  f"one node solve per step"},
+           "cpu_baseline": {"value": val, "unit": "node_solves/s", "cores": _blas_threads(), "kind": "port", "sample": sample},
            "e2e": {"value": val, "unit": "node_solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-def outer_iteration(fs, ctx, contour, generalized=True):
+def rr_phase(ctx, generalized=True):
     from feastsolver_jl_b200.feast import _eig_sorted
     Aq, Bq = ctx.project(generalized)
     Lam, Xq = _eig_sorted(Aq, Bq)
     res = ctx.recover_residual(Xq, Lam)
-    st = ctx.contour_apply(Lam)
-    return Lam, res, st
+    return Lam, res
+
+
+def e2e_solve(fs, A, B, contour, X0, solver_opts, device, hook):
+    """The public call with HOST buffers, run to convergence (context creation, operator upload, layout build, all
+    outer iterations and the download of X inside the timed region)."""
+    st = {}
+    Xh = X0.copy()
+    t0 = time.perf_counter()
+    ctx = fs.FeastContext(device=device)
+    e, v, rs = fs.gen_feast(Xh, A, B, contour, eps=EPS, iter=10, ctx=ctx, solver_opts=solver_opts, stats=st, comm=hook)
+    ctx.close()
+    return e, rs, st, time.perf_counter() - t0
 
 
 def run_ours(args):
@@ -195,7 +215,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import feastsolver_jl_b200 as fs
-    from feastsolver_jl_b200 import _lib
+    from feastsolver_jl_b200 import _lib, workloads as wl
+    from feastsolver_jl_b200.contour import in_contour
     from feastsolver_jl_b200.distributed import make_comm_hook
     from feastsolver_jl_b200.partition import node_owners
 
@@ -204,19 +225,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def reduce_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def max_over_ranks(x):
+        return reduce_ranks(x, dist.ReduceOp.MAX) if world > 1 else x
+
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return reduce_ranks(x, dist.ReduceOp.SUM) if world > 1 else x
 
     grid = args.grid
     A, B, c, r, cnt, X0 = build_workload(grid)
@@ -228,6 +248,7 @@ def run_ours(args):
                    "precond": {"auto": _lib.PRECOND_AUTO, "none": _lib.PRECOND_NONE, "amg": _lib.PRECOND_AMG}[args.precond]}
 
     ctx = fs.FeastContext(device=local)
+    ctx.set_solver(**solver_opts)
     ctx.set_operator(0, A)
     ctx.set_operator(1, B)
     ctx.set_problem(_lib.PROBLEM_GENERALIZED, 2, n)
@@ -235,26 +256,39 @@ def run_ours(args):
         hook(ctx)
     ctx.set_contour(contour.nodes, contour.weights)
     ctx.set_node_owners(owners)
-    ctx.set_solver(**solver_opts)
     if args.mixed_prec:
-        ctx.set_mixed_precision(True)     # experimental: complex64 COCG blocks (the reference's mixed_prec=true)
+        ctx.set_mixed_precision(True)     # complex64 COCG blocks (the reference's mixed_prec=true); unpreconditioned path
     ctx.set_subspace(X0)
     layout = ctx.layout_info()
     pinfo = ctx.preconditioner_info()
 
-    for _ in range(args.warmup):
-        outer_iteration(fs, ctx, contour)
-    ctx.set_subspace(X0)          # timed steps are the first K iterations of the real solve
+    def converged(Lam, res):
+        ins = in_contour(Lam, contour)
+        return bool(ins.any() and res[ins].max() < EPS)
 
+    for _ in range(args.warmup):
+        Lam, res = rr_phase(ctx)
+        ctx.contour_apply(Lam)
+    ctx.set_subspace(X0)
+
+    # ---- timed region: K steps, every one a REAL (pre-convergence) outer iteration of the solve from X0.  When the
+    # solve converges inside the region it is restarted from X0 (the re-upload and its Rayleigh-Ritz phase stay inside the
+    # bracket), so no post-convergence pass -- which would need fewer inner iterations -- is ever timed.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
-    agg = {"inner_iters_total": 0, "t_spmm_ms": 0.0, "spmm_launches": 0, "t_solve_ms": 0.0, "t_reduce_ms": 0.0}
+    agg = {"inner_iters_total": 0, "t_spmm_ms": 0.0, "spmm_launches": 0, "t_solve_ms": 0.0, "t_factor_ms": 0.0, "t_reduce_ms": 0.0}
+    restarts = 0
     barrier()
     ctx.timer_start()
     for _ in range(args.steps):
-        Lam, res, st = outer_iteration(fs, ctx, contour)
+        Lam, res = rr_phase(ctx)
+        if converged(Lam, res):
+            ctx.set_subspace(X0)
+            restarts += 1
+            Lam, res = rr_phase(ctx)
+        st = ctx.contour_apply(Lam)
         for k in agg:
             agg[k] += st[k]
     ms = ctx.timer_stop()
@@ -262,41 +296,38 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
     launches = int(sum_over_ranks(ctx.launch_count() - launches0))
-    spmm_ms_rank = agg["t_spmm_ms"] / max(1, agg["spmm_launches"])
-    spmm_ms = max_over_ranks(spmm_ms_rank)
+    spmm_ms = max_over_ranks(agg["t_spmm_ms"] / max(1, agg["spmm_launches"]))
     inner_total = int(sum_over_ranks(agg["inner_iters_total"]))
     reduce_ms = max_over_ranks(agg["t_reduce_ms"])
+    solve_ms_max, solve_ms_sum = max_over_ranks(agg["t_solve_ms"] + agg["t_factor_ms"]), sum_over_ranks(agg["t_solve_ms"] + agg["t_factor_ms"])
     value = NODES * args.steps / (ms / 1e3)
+    # ---- dominant vector kernel of the Krylov iteration, timed alone on the resident blocks (CUDA events, library stream)
+    vec_ms = ctx.kernel_time("cocg_direction", reps=20) if rank == 0 else None
     ctx.close()
 
     if args.no_e2e:
         if rank == 0:
             print(json.dumps({"metric": "contour_node_solves_per_sec", "value": value, "ms_per_step": ms / args.steps,
                               "spmm_ms_per_launch": spmm_ms, "gpu_launches": launches, "inner_iters_per_step": inner_total / args.steps,
-                              "preconditioner": pinfo, "note": "profiling run (--no-e2e)"}))
+                              "preconditioner": pinfo, "vector_kernel_ms": vec_ms, "note": "profiling run (--no-e2e)"}))
         if world > 1:
             dist.destroy_process_group()
         return
     # ---- e2e: public API with host buffers, run to convergence (time-to-solution) ----
-    st_e2e = {}
-    Xh = X0.copy()
     barrier()
     t0 = time.perf_counter()
-
-    ctx2 = fs.FeastContext(device=local)
-    e, v, rs = fs.gen_feast(Xh, A, B, contour, eps=EPS, iter=10, ctx=ctx2, solver_opts=solver_opts, stats=st_e2e,
-                            comm=hook)
+    e, rs, st_e2e, _ = e2e_solve(fs, A, B, contour, X0, solver_opts, local, hook)
     barrier()
     tts = max_over_ranks(time.perf_counter() - t0)
-    ctx2.close()
     iters_with_solves = sum(1 for h in st_e2e["history"] if "nodes_local" in h)
     e2e_val = NODES * iters_with_solves / tts
     h2d = (A.data.nbytes + A.indices.nbytes * 2 + A.indptr.nbytes * 2) * 2 + X0.nbytes  # int64 indices cross the ABI
     d2h = X0.nbytes
-    from feastsolver_jl_b200 import workloads as wl
     exact = wl.laplacian3d_spectrum(grid, count=cnt + 8)
     exact = exact[np.abs(exact - c) <= r]
     eig_err = float(np.abs(np.sort(e.real) - exact).max() / np.abs(exact).max()) if e.size == exact.size else None
+    phases = {k: (round(v, 4) if not isinstance(v, list) else [round(x, 4) for x in v]) for k, v in st_e2e["phases"].items()}
+    phases_max = {k: max_over_ranks(v) for k, v in st_e2e["phases"].items() if not isinstance(v, list)} if world > 1 else None
 
     if rank != 0:
         if world > 1:
@@ -310,6 +341,7 @@ def run_ours(args):
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
+    vec_bytes = 5 * 16 * n * M0   # x, p read + written, z read: the direction kernel of the (preconditioned) COCG iteration
     out = {
         "metric": "contour_node_solves_per_sec", "value": value, "unit": "node_solves/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -317,27 +349,169 @@ def run_ours(args):
         "config": {"workload": f"C2: sparse generalized Hermitian 3-D Laplacian+mass pencil, grid {grid}^3 (n={n}, "
                                f"nnz={A.nnz}), lowest slice ({cnt} eigenvalues), m0={M0}, {NODES} Gauss-Legendre nodes "
                                f"sharded over {world} GPU(s); step = one outer FEAST iteration ({NODES} node solves + RR)",
-                   "inner_solver": f"pseudo-block COCG, rel tol {INNER_TOL}" + (", complex64 blocks (mixed_prec, steady-state leg only)" if args.mixed_prec else ""), "l2_policy": "inputs (5 GB of Krylov blocks) exceed the 126 MB L2",
+                   "inner_solver": ("pseudo-block COCG" + (" preconditioned by a smoothed-aggregation V(1,1) cycle, levels "
+                                    + "/".join(str(v) for v in pinfo["sizes"]) if pinfo["levels"] else "")
+                                    + f", rel tol {INNER_TOL}" + (", complex64 blocks (mixed_prec)" if args.mixed_prec else "")),
+                   "timed_steps": "real pre-convergence passes only (solve restarted from X0 when it converges inside the "
+                                  f"timed region; {restarts} restart(s))",
+                   "l2_policy": "inputs (5 GB of Krylov blocks) exceed the 126 MB L2",
                    "node_owners": [int(o) for o in owners],
                    "layout": {"rows_renumbered": layout["reordered"], "spmm_tiles": layout["ntiles"],
                               "halo_rows_per_row": round(layout["halo_rows_per_row"], 3)}},
+        "value_real_passes": value,
         "time_to_solution_s": tts, "outer_iterations": len(st_e2e["history"]), "eigenvalues_found": int(e.size),
         "eigenvalues_exact": int(exact.size), "max_residual": float(rs.max()) if rs.size else None,
         "eig_rel_err_vs_analytic": eig_err, "inner_iters_per_step": inner_total / args.steps,
+        "ms_per_inner_iteration": (solve_ms_sum / max(1, inner_total)),
         "allreduce_ms_per_step": reduce_ms / args.steps,
+        "node_solve_ms_per_step": {"max_over_ranks": solve_ms_max / args.steps, "mean_over_ranks": solve_ms_sum / world / args.steps},
         "e2e": {"value": e2e_val, "unit": "node_solves/s", "h2d_bytes_per_step": int(h2d / max(1, iters_with_solves)),
                 "d2h_bytes_per_step": int(d2h / max(1, iters_with_solves)), "time_to_solution_s": tts,
-                "api": "feastsolver_jl_b200.gen_feast(X, A, B, contour) with host numpy/scipy buffers, to convergence"},
+                "api": "feastsolver_jl_b200.gen_feast(X, A, B, contour) with host numpy/scipy buffers, to convergence",
+                "phases_rank0_s": phases, "phases_max_over_ranks_s": phases_max,
+                "preconditioner_setup_s": st_e2e["preconditioner"]["setup_s"]},
         "gpu_launches": launches,
         "roofline": {"kernel": "spmm_tiled_kernel<c128, DOT> (COCG q = (A - zB) p, fused <p,q>)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "bytes_per_launch": bytes_per_launch, "ms_per_launch": spmm_ms,
-                     "share_of_step": (agg["t_spmm_ms"] / ms) if world == 1 else None},
+                     "share_of_step": (agg["t_spmm_ms"] / ms) if world == 1 else None,
+                     "note": "timed inside the solves (events around every q = Zp launch); the V-cycle launches the same kernel twice more per iteration"},
+        "roofline_vector_kernel": {"kernel": "cocg_p_kernel (x += alpha p ; p = z + beta p)", "bound": "hbm",
+                                   "achieved": vec_bytes / (vec_ms * 1e-3) / 1e9 if vec_ms else None, "peak": peak, "unit": "GB/s",
+                                   "frac": (vec_bytes / (vec_ms * 1e-3) / 1e9 / peak) if vec_ms else None,
+                                   "bytes_per_launch": vec_bytes, "ms_per_launch": vec_ms,
+                                   "note": "timed alone on the resident blocks after the timed region (20 launches, CUDA events)"},
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu:
-        out["cpu_baseline"] = cpu_sample(8)
+        # like-for-like leg: BOTH arms on the same pencil at the largest CPU-feasible grid (cap: CPU_BUDGET_S of host time)
+        g, t20 = pick_cpu_grid(1, CPU_BUDGET_S, candidates=(SAME_GRID, 40, 32, 24))
+        cpu = cpu_sample(g, 1)
+        A2, B2, c2, r2, cnt2, X2 = build_workload(g)
+        ct2 = fs.circular_contour_gauss(c2, r2, NODES)
+        e2, rs2, st2, tts2 = e2e_solve(fs, A2, B2, ct2, X2, solver_opts, local, None)
+        it2 = sum(1 for h in st2["history"] if "nodes_local" in h)
+        out["cpu_baseline"] = cpu
+        out["same_config"] = {
+            "workload": f"C2 pencil on a {g}^3 grid (n={g**3}), m0={M0}, {NODES} Gauss nodes, lowest slice ({cnt2} eigenvalues)",
+            "same_config": True, "grid_cap": f"largest of {SAME_GRID}/40/32/24 whose sparse LU fits {CPU_BUDGET_S:.0f} s on this host "
+                                             f"(one 20^3 node solve took {t20:.2f} s)",
+            "gpu_e2e_node_solves_per_s": NODES * it2 / tts2, "gpu_time_to_solution_s": tts2, "gpu_eigenvalues_found": int(e2.size),
+            "gpu_max_residual": float(rs2.max()) if rs2.size else None,
+            "cpu_node_solves_per_s": cpu["value"], "cpu_cores": cpu["cores"], "cpu_sample": "1 node solve (factor + 64-rhs solve)",
+            "e2e_ratio_gpu_over_cpu": (NODES * it2 / tts2) / cpu["value"]}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------ C3 (dense) line
+def fp64_tensor_peak(torch, N=8192):
+    """FP64 tensor-pipe denominator measured in THIS run: cuBLAS ZGEMM N^3 through torch (8 N^3 real flops), best of 3."""
+    a = torch.randn(N, N, dtype=torch.complex128, device="cuda")
+    b = torch.randn(N, N, dtype=torch.complex128, device="cuda")
+    (a @ b)
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        (a @ b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 8.0 * N ** 3 / (best * 1e-3) / 1e12
+
+
+def run_c3(args):
+    """BASELINE config 3: dense non-Hermitian complex n = 16384, circular contour, m0 = 128, 32 trapezoid nodes, feast!
+    with store=true (one LU per node, reused by every outer iteration).  python bench.py --config C3 [--gpus N]"""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import feastsolver_jl_b200 as fs
+    from feastsolver_jl_b200 import workloads as wl
+    from feastsolver_jl_b200.distributed import make_comm_hook
+    n, m0, nodes, rad = (args.grid if args.grid_given else 16384), 128, 32, 7.0
+    peak = fp64_tensor_peak(torch) if rank == 0 else None
+    A = wl.dense_nonhermitian(n, seed=1551)
+    X0 = wl.rand_subspace(n, m0, seed=0)
+    hook = make_comm_hook()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    st = {}
+    t0 = time.perf_counter()
+    e, v, res = fs.feast(X0, A, nodes=nodes, iter=10, c=0.0, r=rad, eps=1e-12, store=True, stats=st, comm=hook)
+    torch.cuda.synchronize()
+    tts = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    hist = [h for h in st["history"] if "nodes_local" in h]
+
+    def red(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+    tts = red(tts, dist.ReduceOp.MAX) if world > 1 else tts
+    t_factor = red(sum(h["t_factor_ms"] for h in hist), dist.ReduceOp.MAX) if world > 1 else sum(h["t_factor_ms"] for h in hist)
+    t_solve = red(sum(h["t_solve_ms"] for h in hist), dist.ReduceOp.MAX) if world > 1 else sum(h["t_solve_ms"] for h in hist)
+    t_pass = red(sum(h["t_total_ms"] for h in hist), dist.ReduceOp.MAX) if world > 1 else sum(h["t_total_ms"] for h in hist)
+    launches = int(red(st["launches"], dist.ReduceOp.SUM)) if world > 1 else int(st["launches"])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    steps = len(hist)
+    local_nodes = nodes // world
+    lu_tf = (8.0 / 3.0) * n ** 3 * local_nodes / (t_factor * 1e-3) / 1e12 if t_factor else None
+    getrs_tf = 8.0 * n ** 2 * m0 * local_nodes * steps / (t_solve * 1e-3) / 1e12 if t_solve else None
+    out = {"metric": "contour_node_solves_per_sec", "value": nodes * steps / (t_pass * 1e-3), "unit": "node_solves/s", "n_gpus": world,
+           "steps": steps, "warmup": 0, "ms_per_step": t_pass / max(1, steps), "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+           "config": {"workload": f"C3: dense non-Hermitian complex n={n} standard problem, circular contour r={rad}, m0={m0}, "
+                                  f"{nodes} trapezoid nodes sharded over {world} GPU(s), feast! with store=true; step = one outer "
+                                  f"iteration ({nodes} node solves; the {nodes} LU factorisations happen in the first one)",
+                      "l2_policy": "operands (4.3 GB per matrix) exceed the 126 MB L2"},
+           "time_to_solution_s": tts, "outer_iterations": len(st["history"]), "eigenvalues_found": int(e.size),
+           "max_residual": float(res.max()) if res.size else None,
+           "e2e": {"value": nodes * steps / tts, "unit": "node_solves/s", "h2d_bytes_per_step": int((A.nbytes + X0.nbytes) / max(1, steps)),
+                   "d2h_bytes_per_step": int(X0.nbytes / max(1, steps)), "time_to_solution_s": tts,
+                   "api": "feastsolver_jl_b200.feast(X, A; nodes, c, r, store=true) with host numpy buffers, to convergence",
+                   "phases_rank0_s": {k: (round(x, 3) if not isinstance(x, list) else [round(y, 3) for y in x]) for k, x in st["phases"].items()}},
+           "gpu_launches": launches,
+           "roofline": {"kernel": "dense LU (lu_panel_kernel + laswp + trsm + zgemm_dmma_kernel trailing updates)", "bound": "tensor",
+                        "achieved": lu_tf, "peak": peak, "peak_source": "cuBLAS ZGEMM 8192^3 through torch, measured in this run (FP64 tensor pipe)",
+                        "unit": "TFLOP/s", "frac": (lu_tf / peak) if (lu_tf and peak) else None, "traffic": None,
+                        "flops_per_launch": (8.0 / 3.0) * n ** 3, "getrs_tflops": getrs_tf,
+                        "getrs_frac": (getrs_tf / peak) if (getrs_tf and peak) else None},
+           "clocks": clocks}
+    if world == 1 and not args.no_cpu:
+        import scipy.linalg as sla
+        nc = min(n, 8192)    # bounded sample: LU + m0-rhs solve at n = 8192 (1/8 of the flops of one C3 node solve)
+        Z = A[:nc, :nc] - (0.3 + 0.7j) * np.eye(nc)
+        t0 = time.perf_counter()
+        lu = sla.lu_factor(Z, check_finite=False)
+        sla.lu_solve(lu, X0[:nc], check_finite=False)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "node_solves/s", "cores": _blas_threads(), "kind": "port",
+                               "sample": f"1 node solve (zgetrf + {m0}-rhs zgetrs through scipy/OpenBLAS, the reference's LAPACK path) of the leading "
+                                         f"{nc} x {nc} block: {(nc / n) ** 3:.3f} of the flops of a C3 node solve", "seconds": dt,
+                               "tflops": ((8.0 / 3.0) * nc ** 3 + 8.0 * nc ** 2 * m0) / dt / 1e12}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -349,7 +523,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--grid", type=int, default=GRID, help="grid points per dimension (default: the C2 size 100)")
+    ap.add_argument("--grid", type=int, default=None, help="grid points per dimension (default: the C2 size 100)")
+    ap.add_argument("--config", default="C2", choices=["C2", "C3"], help="C2 (default, the headline) or C3 (dense n=16384 line)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs only)")
     ap.add_argument("--precond", default="auto", choices=["auto", "none", "amg"],
@@ -357,10 +532,13 @@ def main():
     ap.add_argument("--mixed-prec", action="store_true",
                     help="EXPERIMENTAL: complex64 storage of the COCG blocks in the steady-state leg (not the headline configuration)")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
-        args.warmup = max(args.warmup, 0)
+    args.grid_given = args.grid is not None
+    if args.grid is None:
+        args.grid = GRID
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "C3":
+        run_c3(args)
     else:
         run_ours(args)
 

@@ -91,6 +91,7 @@ SIGNATURES = {
     "feast_solve": (_i, [_vp, _vp, _i64, _i, _vp, _i64, _vp, _i64, _i]),
     "feast_factor_free": (_i, [_vp, _vp]),
     "feast_apply_operator": (_i, [_vp, _i, _i, _vp, _i64, _i, C.POINTER(C.c_float)]),
+    "feast_kernel_bench": (_i, [_vp, _i, _i, C.POINTER(C.c_float)]),
     "feast_sync": (_i, [_vp]),
     "feast_timer_start": (_i, [_vp]),
     "feast_timer_stop": (_i, [_vp, C.POINTER(C.c_float)]),

@@ -1744,6 +1744,14 @@ int feast_apply_operator(feast_ctx* ctx, int slot, int which, feast_c128* Y, int
     return 0;
 }
 
+int feast_kernel_bench(feast_ctx* ctx, int which, int reps, float* ms) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, which == 0 || which == 1, 2, "which must be 0 (direction kernel) or 1 (residual update kernel)");
+    ARG_CHECK(ctx, reps >= 1, 3, "reps must be positive");
+    ARG_CHECK(ctx, ms != nullptr, 4, "null output");
+    return krylov_kernel_bench(ctx, which, reps, ms);
+}
+
 int feast_sync(feast_ctx* ctx) {
     ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
     FEAST_TRY(bind_device(ctx));

@@ -450,6 +450,49 @@ int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs,
     return 0;
 }
 
+// =============================================================================== stand-alone kernel timing
+namespace {
+__global__ void bench_scalars_kernel(int m, KryScal s) {
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        s.alpha[j] = cmake(1e-30, 0.0);   // non-zero: the column counts as active in this iteration
+        s.beta[j] = cmake(0.5, 0.0);
+        s.active[j] = 1;
+    }
+}
+}  // namespace
+
+// Times `reps` launches of one vector kernel of the Krylov iteration on the resident work blocks (CUDA events on the
+// library stream): which = 0 the direction kernel (x += alpha p ; p = z + beta p, 5 block passes), 1 the residual update
+// (r -= alpha q with the fused norm partials, 3 block passes).  bench.py reports their HBM roofline beside the SpMM's.
+int krylov_kernel_bench(feast_ctx* ctx, int which, int reps, float* ms) {
+    if (!ctx->kr.p || !ctx->kp.p || !ctx->kq.p || !ctx->W1.p)
+        return feast_fail(ctx, FEAST_ERR_STATE, "the Krylov work blocks do not exist yet (run a contour pass first)");
+    const int64_t n = ctx->n;
+    const int m = ctx->m0;
+    const int64_t total = n * m;
+    KryScal s = carve_scalars(ctx);
+    cudaStream_t st = ctx->stream;
+    bench_scalars_kernel<<<1, 128, 0, st>>>(m, s);
+    KLAUNCH_CHECK(ctx);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->W1.p, 0, sizeof(c128) * total, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->kp.p, 0, sizeof(c128) * total, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->kr.p, 0, sizeof(c128) * total, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->kq.p, 0, sizeof(c128) * total, st));
+    const int rgrid = red_grid_k(n, m);
+    for (int rep = -2; rep < reps; ++rep) {   // two warm-up launches
+        if (rep == 0) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+        if (which == 0) cocg_p_kernel<<<ew_grid_k(total), 256, 0, st>>>(total, m, ctx->W1.p, ctx->kp.p, ctx->kr.p, s);
+        else cocg_update_kernel<<<rgrid, 256, 768 * sizeof(double), st>>>(n, m, ctx->kr.p, ctx->kq.p, s, ctx->red_d);
+        KLAUNCH_CHECK(ctx);
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+    float t = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+    *ms = t / (float)(reps > 0 ? reps : 1);
+    return 0;
+}
+
 // =============================================================================== preconditioned COCG
 // COCG with the smoothed-aggregation V-cycle (amg.cu) as a complex symmetric preconditioner M^-1:
 //     z = M^-1 r ; rho = <r, z> ; p = z + beta p ; q = Z p ; alpha = rho / <p, q> ; x += alpha p ; r -= alpha q

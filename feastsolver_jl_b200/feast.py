@@ -17,6 +17,7 @@ import ctypes as C
 import numpy as np
 import scipy.linalg as sla
 import scipy.sparse as sp
+from scipy.sparse.linalg import norm as spla_norm
 
 from . import _lib
 from ._lib import FeastError, FeastStats
@@ -189,6 +190,44 @@ class FeastContext:
         self.last_stats["warn_inner_maxit"] = rc == _lib.FEAST_WARN_INNER_MAXIT
         return self.last_stats
 
+    # -- sampled operators (opaque T(z) closures)
+    def set_sample(self, M):
+        """Replace the sample T(point) held in slot 0 of a PROBLEM_SAMPLED problem (same shape / storage class)."""
+        if sp.issparse(M):
+            M = sp.csc_matrix(M)
+            M.sort_indices()
+            is_c = np.iscomplexobj(M.data)
+            data = np.ascontiguousarray(M.data, dtype=np.complex128 if is_c else np.float64)
+            indptr = np.ascontiguousarray(M.indptr, dtype=np.int64)
+            indices = np.ascontiguousarray(M.indices, dtype=np.int64)
+            self._ck(self.lib.feast_set_sample_csc(self.h, M.shape[0], _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data),
+                                                   int(is_c), 0))
+            return
+        M = np.asarray(M)
+        is_c = np.iscomplexobj(M)
+        Mf = np.asfortranarray(M, dtype=np.complex128 if is_c else np.float64)
+        self._ck(self.lib.feast_set_sample_dense(self.h, Mf.shape[0], _lib.ptr(Mf), Mf.shape[0], int(is_c)))
+
+    def contour_node(self, k, lam, first_pass, phase):
+        st = FeastStats()
+        lam_p = None
+        if lam is not None:
+            lam = np.ascontiguousarray(lam, dtype=np.complex128)
+            lam_p = _lib.ptr(lam)
+        rc = self.lib.feast_contour_node(self.h, int(k), lam_p, int(first_pass), int(phase), C.byref(st))
+        self._ck(rc, allow=(0, _lib.FEAST_WARN_INNER_MAXIT))
+        self.last_stats = st.as_dict()
+        self.last_stats["warn_inner_maxit"] = rc == _lib.FEAST_WARN_INNER_MAXIT
+        return self.last_stats
+
+    def node_needs_sample(self, k):
+        return self.lib.feast_node_needs_sample(self.h, int(k)) != 0
+
+    def sampled_residual(self, j, fro):
+        res = C.c_double(0.0)
+        self._ck(self.lib.feast_sampled_residual(self.h, int(j), float(fro), C.byref(res)))
+        return float(res.value)
+
     def beyn_reduce(self):
         m = self.m0
         Rf = np.empty((m, m), np.complex128, order="F")
@@ -276,6 +315,12 @@ class FeastContext:
                                                C.byref(ms) if reps > 0 else None))
         return Y, float(ms.value)
 
+    def kernel_time(self, which="cocg_direction", reps=20):
+        """Mean device ms of one stand-alone launch of a Krylov vector kernel on the resident blocks (measurement only)."""
+        ms = C.c_float(0.0)
+        self._ck(self.lib.feast_kernel_bench(self.h, {"cocg_direction": 0, "cocg_update": 1}[which], int(reps), C.byref(ms)))
+        return float(ms.value)
+
     def sync(self):
         self._ck(self.lib.feast_sync(self.h))
 
@@ -335,31 +380,43 @@ def iter_debug_print(nit, Lam, res, contour, spurious=1e-5):
 
 def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, generalized, stats_out, comm,
                    mixed_prec=False):
+    import time as _time
     N, m0 = X.shape
     if A.shape[0] != A.shape[1]:
         raise ValueError("Incorrect dimensions of A, must be square")  # feast.jl:13
     if A.shape[0] != N:
         raise ValueError("Incorrect dimensions of X, must match A")  # feast.jl:15
+    ph = {}          # wall-clock phase breakdown of the call (seconds), returned in stats["phases"]
+    t_last = [_time.perf_counter()]
+
+    def tick(name):
+        now = _time.perf_counter()
+        ph[name] = ph.get(name, 0.0) + (now - t_last[0])
+        t_last[0] = now
+
     own_ctx = ctx is None
     if own_ctx:
         ctx = FeastContext()
+    tick("ctx_create_s")
     try:
         A, B = _densify_if_mixed(A, B)
+        ctx.set_solver(store=store, **solver_opts)   # before the operators: the device layout is then built once
         ctx.set_operator(0, A)
         if generalized:
             ctx.set_operator(1, B, n=N)
-            ctx.set_problem(_lib.PROBLEM_GENERALIZED, 2, N)
-        else:
-            ctx.set_problem(_lib.PROBLEM_STANDARD, 1, N)
+        tick("upload_operators_s")                   # host CSC -> CSR (+ symmetry check), dense uploads
+        ctx.set_problem(_lib.PROBLEM_GENERALIZED if generalized else _lib.PROBLEM_STANDARD, 2 if generalized else 1, N)
+        tick("build_layout_s")                       # union pattern, tile plan, multigrid hierarchy, uploads
         if comm is not None:
             comm(ctx)
+        tick("comm_init_s")
         ctx.set_contour(contour.nodes, contour.weights)
         if ctx.nranks > 1:  # balanced node -> rank map (near-axis nodes cost more Krylov iterations)
             ctx.set_node_owners(node_owners(contour.nodes, ctx.nranks))
-        ctx.set_solver(store=store, **solver_opts)
         if mixed_prec:
-            ctx.set_mixed_precision(True)   # feast.jl:19-25 (experimental on the device: complex64 COCG blocks)
+            ctx.set_mixed_precision(True)   # feast.jl:19-25 (complex64 COCG blocks on the device)
         ctx.set_subspace(X)
+        tick("upload_subspace_s")
         Lam = np.zeros(m0, complex)
         res = np.zeros(m0)
         hist = []
@@ -367,6 +424,7 @@ def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, 
             Aq, Bq = ctx.project(generalized)  # feast.jl:41-43 / 117-121
             Lam, Xq = _eig_sorted(Aq, Bq)  # feast.jl:45-47 / 122-124 (host LAPACK)
             res = ctx.recover_residual(Xq, Lam)  # feast.jl:48-50 / 125-127
+            tick("rayleigh_ritz_s")
             inside = in_contour(Lam, contour)
             if debug:
                 iter_debug_print(nit, Lam, res, contour, 1e-5)
@@ -380,14 +438,19 @@ def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, 
             if nit < iter:  # feast.jl:57
                 st = ctx.contour_apply(Lam)
                 rec.update(st)
+                tick("contour_passes_s")
+                ph.setdefault("contour_pass_s", []).append(st["t_total_ms"] / 1e3)
             hist.append(rec)
         X[:, :] = ctx.get_X()
+        tick("download_s")
         if stats_out is not None:
             stats_out["history"] = hist
             stats_out["Lam_all"] = Lam
             stats_out["res_all"] = res
             stats_out["launches"] = ctx.launch_count()
             stats_out["phase_ms"] = ctx.phase_times()
+            stats_out["phases"] = ph
+            stats_out["preconditioner"] = ctx.preconditioner_info()
     finally:
         if own_ctx:
             ctx.close()
@@ -429,31 +492,40 @@ def nlfeast(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=1
             _stop_rule="nlfeast"):
     """nlfeast!(T, X, nodes, iter; ...)  (src/nlfeast.jl:2-84) -> (L, X, res), all m0, unfiltered.
 
-    ADDED METHOD: `T` is the list of polynomial coefficient matrices
-    [A_0, ..., A_d] with T(z) = sum z^i A_i, so that assembly, solves and residuals run
-    on the device.  An opaque callable cannot be evaluated on the GPU and is rejected.
+    `T` is either the reference's callable z -> N x N matrix (dense ndarray or scipy sparse), or -- ADDED METHOD
+    (SURVEY 8b), the fast path -- the list of polynomial coefficient matrices [A_0, ..., A_d] with
+    T(z) = sum z^i A_i, so that assembly, solves and residuals all run on the device.  A callable is evaluated on the
+    HOST: once per contour node (and only in the first pass when store=true keeps the factorisations) and once per
+    Ritz value for the residuals (src/utils.jl:107,154 do the same m0 evaluations), each sample being uploaded.
     """
     _check_plugins(factorizer, left_divider, False)
-    if callable(T):
-        raise TypeError("nlfeast on the B200 path needs polynomial coefficients [A_0, ..., A_d]; "
-                        "an opaque closure T(z) can only be evaluated on the host")
-    coeffs = list(T)
+    sampled = callable(T)
+    coeffs = None if sampled else list(T)
     N, m0 = X.shape
-    if any(sp.issparse(a) for a in coeffs) and not all(sp.issparse(a) for a in coeffs):
+    if not sampled and any(sp.issparse(a) for a in coeffs) and not all(sp.issparse(a) for a in coeffs):
         coeffs = [a.toarray() if sp.issparse(a) else np.asarray(a) for a in coeffs]
     own_ctx = ctx is None
     if own_ctx:
         ctx = FeastContext()
     try:
-        for i, Ai in enumerate(coeffs):
-            ctx.set_operator(i, Ai, n=N)
-        ctx.set_problem(_lib.PROBLEM_POLYNOMIAL, len(coeffs), N)
+        contour = circular_contour_trapezoidal(c, r, nodes)  # nlfeast.jl:8 hard-wires circle + trapezoid
+        if sampled:
+            T0 = T(contour.nodes[0])
+            sparse_T = sp.issparse(T0)
+            if T0.shape != (N, N):
+                raise ValueError("Incorrect dimensions of X, must match T")
+            ctx.set_operator(0, T0, n=N)
+            ctx.set_problem(_lib.PROBLEM_SAMPLED, 1, N)
+        else:
+            for i, Ai in enumerate(coeffs):
+                ctx.set_operator(i, Ai, n=N)
+            ctx.set_problem(_lib.PROBLEM_POLYNOMIAL, len(coeffs), N)
         if comm is not None:
             comm(ctx)
-        contour = circular_contour_trapezoidal(c, r, nodes)  # nlfeast.jl:8 hard-wires circle + trapezoid
         ctx.set_contour(contour.nodes, contour.weights)
+        owners = node_owners(contour.nodes, ctx.nranks) if ctx.nranks > 1 else [0] * nodes
         if ctx.nranks > 1:
-            ctx.set_node_owners(node_owners(contour.nodes, ctx.nranks))
+            ctx.set_node_owners(owners)
         sched = getattr(solver_opts, "tol_schedule", None)    # (first pass, later passes): nlfeast_it
         base_opts = dict(solver_opts or {})
         if sched is not None:
@@ -468,7 +540,14 @@ def nlfeast(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=1
             if sched is not None and nit == 1:
                 base_opts["inner_tol"] = sched[1]
                 ctx.set_solver(store=store, **base_opts)   # same solver kind: the device layout is kept
-            st = ctx.contour_apply(Lam if nit > 0 else None, first_pass=(nit == 0))  # nlfeast.jl:36-61
+            if sampled:   # nlfeast.jl:36-61 with T(z_k) evaluated here and uploaded, node by node
+                mine = [k for k in range(nodes) if owners[k] == ctx.rank] or [-1]
+                for i, k in enumerate(mine):
+                    if k >= 0 and ctx.node_needs_sample(k):
+                        ctx.set_sample(T(contour.nodes[k]))
+                    st = ctx.contour_node(k, Lam if nit > 0 else None, nit == 0, (1 if i == 0 else 0) | (2 if i == len(mine) - 1 else 0))
+            else:
+                st = ctx.contour_apply(Lam if nit > 0 else None, first_pass=(nit == 0))  # nlfeast.jl:36-61
             Rf, G1 = ctx.beyn_reduce()  # utils.jl:70-71 (tall part)
             U, S, Vh = sla.svd(Rf, check_finite=False)  # m0 x m0 (host)
             Am = (U.conj().T @ G1) @ Vh.conj().T * (1.0 / S)[None, :]  # utils.jl:71-73
@@ -477,6 +556,12 @@ def nlfeast(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=1
             Lam = np.ascontiguousarray(w[p])
             Xq = U @ v[:, p]  # utils.jl:75  X = U * vectors
             res = ctx.recover_residual(Xq, Lam)  # nlfeast.jl:66-67
+            if sampled:   # update_R! / residuals with T(l_j) evaluated on the host (utils.jl:104-109, 151-157)
+                for j in range(m0):
+                    Tj = T(Lam[j])
+                    ctx.set_sample(Tj)
+                    fro = spla_norm(Tj) if sp.issparse(Tj) else float(np.linalg.norm(Tj))
+                    res[j] = ctx.sampled_residual(j, fro)
             inside = in_contour(Lam, c, r)
             res_inside = res[inside]
             rec = {"nit": nit, "inside": int(inside.sum()),

@@ -202,6 +202,9 @@ FEAST_API int  feast_factor_free(feast_ctx* ctx, feast_factor* F);
  * events on the library stream and returns the mean in *ms (NULL ok).        */
 FEAST_API int  feast_apply_operator(feast_ctx* ctx, int slot, int which, feast_c128* Y, int64_t ldy, int reps, float* ms);
 /* synchronise the library stream */
+/* measurement only: mean device time of `reps` stand-alone launches of a vector kernel of the Krylov iteration on the
+ * resident work blocks (which = 0: x += alpha p ; p = z + beta p, 1: r -= alpha q + norm partials) */
+FEAST_API int  feast_kernel_bench(feast_ctx* ctx, int which, int reps, float* ms);
 FEAST_API int  feast_sync(feast_ctx* ctx);
 /* CUDA-event stopwatch on the library stream (the stream every kernel of this context is
  * launched on): start records an event, stop records a second one, synchronises and returns

@@ -306,6 +306,74 @@ function nlfeast!(T::AbstractVector{<:AbstractMatrix}, X::AbstractMatrix{Complex
     Λ, X, res
 end
 
+# ---------------------------------------------------------------- nonlinear driver, reference signature (closure)
+# nlfeast!(T::Function, X, nodes, iter; ...)  (src/nlfeast.jl:2-84): T is opaque, so it is evaluated HERE -- once per
+# contour node (first pass only when store=true keeps the factorisations) and once per Ritz value for the residuals
+# (src/utils.jl:107,154 evaluate T(λ_j) m0 times as well) -- and each sample is uploaded into slot 0 of a
+# FEAST_PROBLEM_SAMPLED (= 3) problem; solves, accumulation, Beyn reduction and residual columns run on the device.
+function _set_sample!(ctx, M::AbstractMatrix, N)
+    if issparse(M)
+        S = SparseMatrixCSC{eltype(M) <: Complex ? ComplexF64 : Float64, Int64}(M)
+        _ck(ctx, ccall((:feast_set_sample_csc, libfeast), Cint, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}, Cint, Cint),
+                       ctx.h, N, S.colptr, S.rowval, S.nzval, eltype(S) <: Complex, 1))
+    else
+        D = convert(Matrix{eltype(M) <: Complex ? ComplexF64 : Float64}, M)
+        _ck(ctx, ccall((:feast_set_sample_dense, libfeast), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint),
+                       ctx.h, N, D, N, eltype(D) <: Complex))
+    end
+end
+function nlfeast!(T::Function, X::AbstractMatrix{ComplexF64}, nodes::Integer, iter::Integer;
+                  c=complex(0.0, 0.0), r=1.0, debug=false, ϵ=10e-12, store=true, spurious=1e-5, factorizer=lu, left_divider=ldiv!)
+    _check_plugins(factorizer, left_divider, false)
+    N, m₀ = size(X)
+    ctx = FeastCtx()
+    contour = circular_contour_trapezoidal(c, r, nodes)                                 # nlfeast.jl:8
+    z = convert(Vector{ComplexF64}, contour.nodes); w = convert(Vector{ComplexF64}, contour.weights)
+    _set_operator!(ctx, 0, T(z[1]), N)
+    _ck(ctx, ccall((:feast_set_problem, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint), ctx.h, 3, 1))
+    _ck(ctx, ccall((:feast_set_contour, libfeast), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}), ctx.h, nodes, z, w))
+    _ck(ctx, ccall((:feast_set_solver, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cint, Cint), ctx.h, 0, 0, 1e-8, 4000, store))
+    _ck(ctx, ccall((:feast_set_subspace, libfeast), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{ComplexF64}, Int64), ctx.h, N, m₀, X, N))
+    _ck(ctx, ccall((:feast_orthonormalize_X, libfeast), Cint, (Ptr{Cvoid},), ctx.h)) # nlfeast.jl:12-13
+    Λ, res = zeros(ComplexF64, m₀), Array{Float64}(undef, m₀)
+    Rf, G1 = zeros(ComplexF64, m₀, m₀), zeros(ComplexF64, m₀, m₀)
+    for nit = 0:iter
+        for k = 1:nodes                                                                # nlfeast.jl:36-61, node by node
+            if ccall((:feast_node_needs_sample, libfeast), Cint, (Ptr{Cvoid}, Cint), ctx.h, k - 1) != 0
+                _set_sample!(ctx, T(z[k]), N)
+            end
+            phase = (k == 1 ? 1 : 0) | (k == nodes ? 2 : 0)
+            _ck(ctx, ccall((:feast_contour_node, libfeast), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Cint, Cint, Ptr{Cvoid}),
+                           ctx.h, k - 1, Λ, nit == 0, phase, C_NULL); allow=(0, 2000))
+        end
+        _ck(ctx, ccall((:feast_beyn_reduce, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}), ctx.h, Rf, G1))
+        S = svd!(copy(Rf))                                                             # m0 x m0 part of utils.jl:70
+        Am = (S.U' * G1) * S.V * Diagonal(1 ./ S.S)                                    # utils.jl:71-73
+        F = eigen!(Am)                                                                 # utils.jl:74
+        Λ .= F.values
+        Xq = convert(Matrix{ComplexF64}, S.U * F.vectors)                              # utils.jl:75
+        _ck(ctx, ccall((:feast_recover_residual, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Cdouble}),
+                       ctx.h, Xq, Λ, res))                                             # X = Q Xq, normalize!
+        for j = 1:m₀                                                                   # update_R! / residuals, utils.jl:104-109,151-157
+            Tj = T(Λ[j])
+            _set_sample!(ctx, Tj, N)
+            rj = Ref{Cdouble}(0.0)
+            _ck(ctx, ccall((:feast_sampled_residual, libfeast), Cint, (Ptr{Cvoid}, Cint, Cdouble, Ref{Cdouble}), ctx.h, j - 1, norm(Tj), rj))
+            res[j] = rj[]
+        end
+        res_inside = res[in_contour.(Λ, c, r)]
+        if size(res_inside, 1) > 0 && maximum(res_inside) < ϵ
+            break
+        end
+        if nit > 1 && sum(res_inside .< spurious) > 0 && maximum(res_inside[res_inside .< spurious]) < ϵ
+            break
+        end
+    end
+    _ck(ctx, ccall((:feast_get_X, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Int64), ctx.h, X, N))
+    finalize(ctx)
+    Λ, X, res
+end
+
 # ---------------------------------------------------------------- fine-grained plugin path
 # Works with the UNMODIFIED reference drivers:  feast!(X, A; factorizer=B200Factorizer(ctx), left_divider=b200_ldiv!)
 # (src/utils.jl:173-179: F = factorizer(C); left_divider(Y, F, X); finalize!(F)).

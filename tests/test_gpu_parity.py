@@ -459,6 +459,41 @@ def test_nlfeast_sparse_butterfly_matches_dense(fs, nep_fixtures, nlfeast_golden
         assert np.abs(exact - l).min() < 1e-10 * max(1.0, abs(l))
 
 
+@pytest.mark.parametrize("storage", ["dense", "sparse"])
+def test_nlfeast_closure_form(fs, nep_fixtures, nlfeast_golden, storage):
+    """nlfeast!(T::Function, ...) -- the reference signature (src/nlfeast.jl:2-4, test/butterfly.jl:61): T is an opaque
+    callable evaluated on the host per node / per Ritz value and uploaded (PROBLEM_SAMPLED).  Same eigenvalues as the
+    companion linearisation, as the oracle run with the same closure, and as the coefficient-list fast path."""
+    if storage == "dense":
+        coeffs = [csc_unpack(nep_fixtures, f"butterfly{i}").toarray() for i in range(5)]
+    else:
+        coeffs = [csc_unpack(nep_fixtures, f"butterfly{i}") for i in range(5)]
+    calls = []
+
+    def T(z):   # z^4 A4 + z^3 A3 + z^2 A2 + z A1 + A0, as written in test/butterfly.jl:61
+        calls.append(z)
+        return z ** 4 * coeffs[4] + z ** 3 * coeffs[3] + z ** 2 * coeffs[2] + z * coeffs[1] + coeffs[0]
+
+    X0 = nlfeast_golden["butterfly_X0"]
+    lc, Xc, rc = fs.nlfeast(T, X0.copy(), 16, 30, c=1 + 1j, r=0.5, eps=1e-13)
+    ncalls = len(calls)
+    ll, Xl, rl = fs.nlfeast(coeffs, X0.copy(), 16, 30, c=1 + 1j, r=0.5, eps=1e-13)
+    lo, Xo, ro = fo.nlfeast(T, X0.copy(), 16, 30, c=1 + 1j, r=0.5, eps=1e-13)
+    exact = nep_fixtures["butterfly_companion_inside"]
+    good = (np.abs(lc - (1 + 1j)) <= 0.5) & (rc < 1e-8)
+    goodl = (np.abs(ll - (1 + 1j)) <= 0.5) & (rl < 1e-8)
+    goodo = (np.abs(lo - (1 + 1j)) <= 0.5) & (ro < 1e-8)
+    assert good.sum() == goodl.sum() == goodo.sum() == 13
+    for l in lc[good]:
+        assert np.abs(exact - l).min() < 1e-10 * max(1.0, abs(l))
+    match_eigs(lc[good], ll[goodl])
+    match_eigs(lc[good], lo[goodo])
+    assert rc[good].max() <= 10 * max(ro[goodo].max(), 1e-13)
+    assert np.allclose(np.linalg.norm(Xc, axis=0), 1.0)
+    # store=true: the nodes are sampled in the first pass only (dense LU keeps its factors); residuals cost m0 samples per pass
+    assert ncalls < 16 * 6 + X0.shape[1] * 31
+
+
 def test_C4_reduced_butterfly_scaled(fs):
     """C4 shape at reduced size: quartic butterfly with 24 x 24 one-dimensional blocks (n = 576, sparse
     5-point coefficient patterns through the union-pattern kernels), 24 trapezoid nodes, m0 = 24."""
