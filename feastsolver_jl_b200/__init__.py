@@ -9,12 +9,12 @@ from ._lib import FeastError, load as load_library  # noqa: F401
 from .contour import (CircularContour, Contour, CustomContour, RectangularContour,  # noqa: F401
                       circular_contour_gauss, circular_contour_trapezoidal, in_contour,
                       rational_func, rectangular_contour_gauss, rectangular_contour_trapezoidal)
-from .feast import (FeastContext, I, contour_estimate_eig, dual_gen_feast, feast, gen_feast, ifeast, nlfeast,  # noqa: F401
-                    nlfeast_it)
+from .feast import (FeastContext, I, beyn, block_SS, contour_estimate_eig, dual_gen_feast, feast, gen_feast,  # noqa: F401
+                    ifeast, nlfeast, nlfeast_it, nlfeast_moments)
 from .partition import node_owners  # noqa: F401
 
 __all__ = [
-    "feast", "gen_feast", "dual_gen_feast", "nlfeast", "ifeast", "nlfeast_it", "contour_estimate_eig", "FeastContext", "FeastError", "I",
+    "feast", "gen_feast", "dual_gen_feast", "nlfeast", "ifeast", "nlfeast_it", "beyn", "block_SS", "nlfeast_moments", "contour_estimate_eig", "FeastContext", "FeastError", "I",
     "Contour", "CircularContour", "RectangularContour", "CustomContour",
     "circular_contour_trapezoidal", "circular_contour_gauss",
     "rectangular_contour_gauss", "rectangular_contour_trapezoidal",

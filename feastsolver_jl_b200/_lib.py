@@ -20,7 +20,9 @@ SOLVER_AUTO, SOLVER_DENSE_LU, SOLVER_KRYLOV, SOLVER_BANDED_LU = 0, 1, 2, 3
 KRYLOV_AUTO, KRYLOV_COCG, KRYLOV_BICGSTAB, KRYLOV_GMRES = 0, 1, 2, 3
 PROBLEM_STANDARD, PROBLEM_GENERALIZED, PROBLEM_POLYNOMIAL, PROBLEM_SAMPLED = 0, 1, 2, 3
 PRECOND_NONE, PRECOND_AMG, PRECOND_AUTO = 0, 1, 2
+SHARD_AUTO, SHARD_NODES, SHARD_COLUMNS = 0, 1, 2
 MAX_SLOTS = 8
+MAX_MOMENTS = 8
 
 
 class c128(C.Structure):
@@ -31,7 +33,7 @@ class FeastStats(C.Structure):
     _fields_ = [("nodes_local", C.c_int), ("inner_iters_total", C.c_int), ("inner_iters_max", C.c_int),
                 ("info", C.c_int), ("inner_relres_max", C.c_double), ("t_factor_ms", C.c_double),
                 ("t_solve_ms", C.c_double), ("t_reduce_ms", C.c_double), ("t_total_ms", C.c_double),
-                ("t_spmm_ms", C.c_double), ("spmm_launches", C.c_int64), ("precond_levels", C.c_int), ("reserved0", C.c_int)]
+                ("t_spmm_ms", C.c_double), ("spmm_launches", C.c_int64), ("precond_levels", C.c_int), ("col_sharded", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -67,6 +69,7 @@ SIGNATURES = {
     "feast_comm_init": (_i, [_vp, _i, _i, _vp]),
     "feast_set_node_owners": (_i, [_vp, _i, _vp]),
     "feast_set_subspace": (_i, [_vp, _i64, _i, _vp, _i64]),
+    "feast_set_X": (_i, [_vp, _vp, _i64]),
     "feast_get_X": (_i, [_vp, _vp, _i64]),
     "feast_get_Q": (_i, [_vp, _vp, _i64]),
     "feast_get_R": (_i, [_vp, _vp, _i64]),
@@ -78,6 +81,11 @@ SIGNATURES = {
     "feast_contour_node": (_i, [_vp, _i, _vp, _i, _i, C.POINTER(FeastStats)]),
     "feast_node_needs_sample": (_i, [_vp, _i]),
     "feast_sampled_residual": (_i, [_vp, _i, _d, C.POINTER(C.c_double)]),
+    "feast_set_sharding": (_i, [_vp, _i]),
+    "feast_set_moments": (_i, [_vp, _i]),
+    "feast_block_gram": (_i, [_vp, _i, _i, _vp]),
+    "feast_moment_combine": (_i, [_vp, _i, _vp, _i64]),
+    "feast_last_fro": (_i, [_vp, _vp]),
     "feast_beyn_reduce": (_i, [_vp, _vp, _vp]),
     "feast_orthonormalize_X": (_i, [_vp]),
     "feast_dual_set_subspace": (_i, [_vp, _i64, _i, _vp, _i64, _vp, _i64]),

@@ -236,7 +236,7 @@ int amg_build(feast_ctx* ctx, int64_t n, const int64_t* rowptr, const int* col, 
 // per-level work blocks for the current m0 (the V-cycle needs r, y, t on every coarse level)
 int amg_ensure_blocks(feast_ctx* ctx) {
     AmgDev* A = ctx->amg;
-    if (!A || A->m_alloc == ctx->m0) return 0;
+    if (!A || A->m_alloc >= ctx->m0) return 0;
     for (size_t l = 1; l < A->lev.size(); ++l) {
         AmgDevLevel& L = A->lev[l];
         fr(L.r); fr(L.y); fr(L.t);

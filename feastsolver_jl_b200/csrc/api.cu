@@ -113,6 +113,8 @@ void free_blocks(feast_ctx* ctx) {
     BlockVec* all[] = {&ctx->Q, &ctx->X, &ctx->R, &ctx->Q1, &ctx->W1, &ctx->W2, &ctx->Ql, &ctx->Xl, &ctx->Rl, &ctx->kx, &ctx->kr,
                        &ctx->kp, &ctx->kq, &ctx->ks, &ctx->kt, &ctx->kv, &ctx->krh};
     for (auto* b : all) dev_free(b->p);
+    for (auto& b : ctx->mom) dev_free(b.p);
+    ctx->mom.clear();
     dev_free(ctx->stage);
     dev_free(ctx->small_d);
     dev_free(ctx->red_d);
@@ -968,6 +970,79 @@ int feast_set_mixed_precision(feast_ctx* ctx, int on) {
     return 0;
 }
 
+int feast_set_sharding(feast_ctx* ctx, int mode) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, mode >= FEAST_SHARD_AUTO && mode <= FEAST_SHARD_COLUMNS, 2, "unknown sharding mode");
+    ctx->shard_mode = mode;
+    return 0;
+}
+
+// Moment accumulators of the following contour passes: S_p = sum_k w_k z_k^p (...) for p < nmom (0 restores the
+// default: 1 for linear problems, 2 for nonlinear ones).  S_0 and S_1 are the blocks Q and Q1 of the other entries.
+int feast_set_moments(feast_ctx* ctx, int nmom) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, nmom >= 0 && nmom <= FEAST_MAX_MOMENTS, 2, "between 0 (default) and 8 moments");
+    ctx->nmom = nmom;
+    return 0;
+}
+
+static const c128* named_block(feast_ctx* ctx, int id) {   // >= 0: moment S_id ; -1: X ; -2: R
+    if (id == -1) return ctx->X.p;
+    if (id == -2) return ctx->R.p;
+    if (id == 0) return ctx->Q.p;
+    if (id == 1) return ctx->Q1.p;
+    if (id >= 2 && id - 2 < (int)ctx->mom.size()) return ctx->mom[id - 2].p;
+    return nullptr;
+}
+
+// G (m0 x m0, column-major) = block(a)^H block(b); block ids: p >= 0 moment S_p, -1 the subspace block X, -2 R.
+// (Y' * S_p of block_SS!, src/beyn.jl:65-68; the Gram matrices behind the tall SVD of the block-Hankel moment matrix)
+int feast_block_gram(feast_ctx* ctx, int a, int b, feast_c128* G) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, G != nullptr, 4, "null output");
+    const c128 *A = named_block(ctx, a), *B = named_block(ctx, b);
+    if (!A || !B) return feast_fail(ctx, FEAST_ERR_STATE, "block %d or %d does not exist (yet)", a, b);
+    const int m = ctx->m0;
+    FEAST_TRY(launch_gram(ctx, ctx->n, m, A, B, ctx->small_d));
+    CUDA_TRY(ctx, cudaMemcpyAsync(G, ctx->small_d, sizeof(c128) * m * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// X = sum_{p < nblk} S_p W_p, W = [W_0; W_1; ...] (nblk*m0 x m0, column-major, ldw >= nblk*m0)
+// (X = S[:, 1:K] * V * Xq of block_SS!, src/beyn.jl:87; Y = U[1:N, :] * vectors of nlfeast_moments!, nlfeast.jl:231)
+int feast_moment_combine(feast_ctx* ctx, int nblk, const feast_c128* W, int64_t ldw) {
+    FEAST_TRY(check_ready(ctx, true));
+    const int m = ctx->m0;
+    ARG_CHECK(ctx, nblk >= 1 && nblk <= FEAST_MAX_MOMENTS, 2, "nblk out of range");
+    ARG_CHECK(ctx, W != nullptr, 3, "null W");
+    ARG_CHECK(ctx, ldw >= (int64_t)nblk * m, 4, "ldw < nblk * m0");
+    FEAST_TRY(ensure_block(ctx, ctx->W1));
+    FEAST_TRY(ensure_block(ctx, ctx->W2));
+    std::vector<hc128> Wp((size_t)m * m);
+    const int64_t total = ctx->n * m;
+    for (int p = 0; p < nblk; ++p) {
+        const c128* S = named_block(ctx, p);
+        if (!S) return feast_fail(ctx, FEAST_ERR_STATE, "moment %d has not been accumulated", p);
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i < m; ++i) Wp[(size_t)j * m + i] = hc128(W[(size_t)j * ldw + (size_t)p * m + i].re, W[(size_t)j * ldw + (size_t)p * m + i].im);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->small_d, Wp.data(), sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
+        FEAST_TRY(launch_update(ctx, ctx->n, m, S, ctx->small_d, p == 0 ? ctx->W2.p : ctx->W1.p));
+        if (p > 0) FEAST_TRY(launch_axpy(ctx, total, ctx->W1.p, ctx->W2.p));     // W2 += W1
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // Wp is reused
+    }
+    std::swap(ctx->X.p, ctx->W2.p);
+    return 0;
+}
+
+// ||T(l_j)||_F of the last feast_recover_residual of a polynomial problem (absolute residual = res * fro)
+int feast_last_fro(feast_ctx* ctx, double* fro) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, fro != nullptr, 2, "null output");
+    for (int j = 0; j < ctx->m0; ++j) fro[j] = j < (int)ctx->last_fro.size() ? ctx->last_fro[j] : 0.0;
+    return 0;
+}
+
 int feast_layout_info(const feast_ctx* ctx, int* info4, double* halo) {
     if (!ctx) return feast_fail(nullptr, -1, "argument 1 invalid: null context");
     if (info4) { info4[0] = ctx->reordered ? 1 : 0; info4[1] = ctx->ntiles; info4[2] = ctx->bandwidth; info4[3] = ctx->tiles_ok ? 1 : 0; }
@@ -1048,6 +1123,20 @@ int feast_set_subspace(feast_ctx* ctx, int64_t n, int m0, const feast_c128* X, i
     return 0;
 }
 
+// Overwrite the block X only (Q and the moment accumulators keep their contents): the probe block of block_SS!
+// (src/beyn.jl:45) is uploaded this way after the contour pass.
+int feast_set_X(feast_ctx* ctx, const feast_c128* X, int64_t ldx) {
+    FEAST_TRY(check_ready(ctx, true));
+    ARG_CHECK(ctx, X != nullptr, 2, "null X");
+    ARG_CHECK(ctx, ldx >= ctx->n, 3, "ldx < n");
+    const int64_t n = ctx->n;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->stage, sizeof(c128) * n, X, sizeof(c128) * ldx, sizeof(c128) * n, ctx->m0,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    FEAST_TRY(launch_colmajor_to_rowmajor(ctx, n, ctx->m0, ctx->stage, n, ctx->X.p, ctx->perm_d));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int feast_get_X(feast_ctx* ctx, feast_c128* X, int64_t ldx) {
     FEAST_TRY(check_ready(ctx, true));
     ARG_CHECK(ctx, X != nullptr, 2, "null X");
@@ -1101,7 +1190,6 @@ int feast_project(feast_ctx* ctx, feast_c128* Aq, feast_c128* Bq) {
 
 int feast_recover_residual(feast_ctx* ctx, const feast_c128* Xq, const feast_c128* lambda, double* res) {
     FEAST_TRY(check_ready(ctx, true));
-    ARG_CHECK(ctx, Xq != nullptr, 2, "null Xq");
     ARG_CHECK(ctx, lambda != nullptr, 3, "null lambda");
     ARG_CHECK(ctx, res != nullptr, 4, "null res");
     const int64_t n = ctx->n;
@@ -1111,9 +1199,11 @@ int feast_recover_residual(feast_ctx* ctx, const feast_c128* Xq, const feast_c12
     c128* lam_d = ctx->vec_lam();
     double* nrm_d = ctx->vec_nrm();
     double* fro_d = nrm_d + m;
-    CUDA_TRY(ctx, cudaMemcpyAsync(M_d, Xq, sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(lam_d, lambda, sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
-    FEAST_TRY(launch_update(ctx, n, m, ctx->Q.p, M_d, ctx->X.p));          // X = Q Xq            feast.jl:48
+    if (Xq) {   // Xq == NULL: X is taken as it is (feast_moment_combine has produced it)
+        CUDA_TRY(ctx, cudaMemcpyAsync(M_d, Xq, sizeof(c128) * m * m, cudaMemcpyHostToDevice, ctx->stream));
+        FEAST_TRY(launch_update(ctx, n, m, ctx->Q.p, M_d, ctx->X.p));      // X = Q Xq            feast.jl:48
+    }
     debug_check_finite(ctx, ctx->X.p, 2 * n * m, "recover: X = Q Xq");
     FEAST_TRY(launch_colnorm2(ctx, n, m, ctx->X.p, nrm_d));
     FEAST_TRY(launch_colnormalize(ctx, n, m, ctx->X.p, nrm_d));            // x_j /= ||x_j||      utils.jl:113
@@ -1167,7 +1257,11 @@ int feast_recover_residual(feast_ctx* ctx, const feast_c128* Xq, const feast_c12
         FEAST_TRY(launch_colnorm2(ctx, n, m, ctx->R.p, nrm_d));
         CUDA_TRY(ctx, cudaMemcpyAsync(hres, nrm_d, sizeof(double) * 2 * m, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int j = 0; j < m; ++j) res[j] = std::sqrt(hres[j]) / std::sqrt(hres[m + j]);  // utils.jl:154
+        ctx->last_fro.resize(m);
+        for (int j = 0; j < m; ++j) {
+            ctx->last_fro[j] = std::sqrt(hres[m + j]);
+            res[j] = std::sqrt(hres[j]) / ctx->last_fro[j];  // utils.jl:154
+        }
     }
     tm.stop();
     return 0;
@@ -1191,19 +1285,41 @@ static int contour_prepare(feast_ctx* ctx, const feast_c128* lambda, int first_p
     if (*solver == FEAST_SOLVER_KRYLOV) FEAST_TRY(ensure_krylov_work(ctx, *method));
     const int nnodes = (int)ctx->znodes.size();
     if (ctx->store && (int)ctx->stored.size() != nnodes) ctx->stored.resize(nnodes);
+    // Krylov solves have no per-node factorisation to keep together, so with several ranks the COLUMNS of every node's
+    // right-hand side are sharded instead of the nodes: every rank runs all nodes on its m0 / nranks columns.  The load
+    // is then balanced by construction -- with the multigrid preconditioner the near-axis nodes need ~10x the iterations
+    // of the others, which no node -> rank map can balance at 2 nodes per rank -- and the vector work scales with the columns.
+    static const char* shard_env = getenv("FEAST_SHARD");
+    int mode = ctx->shard_mode;
+    if (mode == FEAST_SHARD_AUTO && shard_env) mode = !strcmp(shard_env, "nodes") ? FEAST_SHARD_NODES : (!strcmp(shard_env, "columns") ? FEAST_SHARD_COLUMNS : mode);
+    ctx->col_shard = ctx->nranks > 1 && *solver == FEAST_SOLVER_KRYLOV && ctx->problem != FEAST_PROBLEM_SAMPLED &&
+                     mode != FEAST_SHARD_NODES && ctx->m0 >= 2 * ctx->nranks;
+    const int nmom = ctx->nmom > 0 ? ctx->nmom : (nep ? 2 : 1);
+    if (nmom > 1) FEAST_TRY(ensure_block(ctx, ctx->Q1));
+    if ((int)ctx->mom.size() < nmom - 2) ctx->mom.resize(nmom - 2);
+    for (int p = 2; p < nmom; ++p) FEAST_TRY(ensure_block(ctx, ctx->mom[p - 2]));
+    if (ctx->col_shard) FEAST_TRY(ensure_block(ctx, ctx->W2));
     return 0;
 }
 
+static int contour_nmom(const feast_ctx* ctx) {
+    const bool nep = ctx->problem == FEAST_PROBLEM_POLYNOMIAL || ctx->problem == FEAST_PROBLEM_SAMPLED;
+    return ctx->nmom > 0 ? ctx->nmom : (nep ? 2 : 1);
+}
+static c128* moment_block(feast_ctx* ctx, int p) { return p == 0 ? ctx->Q.p : (p == 1 ? ctx->Q1.p : ctx->mom[p - 2].p); }
+
 static bool contour_can_move_nodes(const feast_ctx* ctx, int solver) {   // stored factors / caller-evaluated samples pin nodes to ranks
-    return ctx->nranks > 1 && ctx->auto_balance && ctx->problem != FEAST_PROBLEM_SAMPLED && !(solver != FEAST_SOLVER_KRYLOV && ctx->store);
+    return ctx->nranks > 1 && ctx->auto_balance && !ctx->col_shard && ctx->problem != FEAST_PROBLEM_SAMPLED &&
+           !(solver != FEAST_SOLVER_KRYLOV && ctx->store);
 }
 
 static int contour_begin(feast_ctx* ctx, int solver) {
     const int64_t n = ctx->n;
     const int m = ctx->m0;
     const bool nep = ctx->problem == FEAST_PROBLEM_POLYNOMIAL || ctx->problem == FEAST_PROBLEM_SAMPLED;
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->Q.p, 0, sizeof(c128) * n * m, ctx->stream));           // feast.jl:58
-    if (nep) CUDA_TRY(ctx, cudaMemsetAsync(ctx->Q1.p, 0, sizeof(c128) * n * m, ctx->stream));  // nlfeast.jl:32-33
+    (void)nep;
+    for (int p = 0; p < contour_nmom(ctx); ++p)                                                // feast.jl:58, nlfeast.jl:32-33
+        CUDA_TRY(ctx, cudaMemsetAsync(moment_block(ctx, p), 0, sizeof(c128) * n * m, ctx->stream));
     if (contour_can_move_nodes(ctx, solver) && ctx->have_costs) rebalance_nodes(ctx);
     ctx->cost_local.assign(ctx->znodes.size(), 0.0);
     return 0;
@@ -1218,19 +1334,34 @@ static int contour_node(feast_ctx* ctx, int k, const feast_c128* lambda, int fir
     c128* d_d = ctx->vec_d();
     std::vector<hc128> d(m);
     hc128 coef[FEAST_MAX_SLOTS];
+    (void)nep;
     const c128* rhs = first_pass ? ctx->X.p : ctx->R.p;
     st.nodes_local++;
+    st.col_sharded = ctx->col_shard ? 1 : 0;
     const hc128 z = ctx->znodes[k], w = ctx->zweights[k];
     node_coefs(ctx, z, coef);
     for (int j = 0; j < m; ++j)
         d[j] = first_pass ? w : w / (z - hc128(lambda[j].re, lambda[j].im));              // feast.jl:60,69
     CUDA_TRY(ctx, cudaMemcpyAsync(d_d, d.data(), sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
     cudaEventRecord(e0, ctx->stream);
-    FEAST_TRY(solve_shifted(ctx, solver, method, k, coef, rhs, ctx->W1.p, st, e1, rc_final));
-    debug_check_finite(ctx, rhs, 2 * n * m, "contour: rhs");
-    debug_check_finite(ctx, ctx->W1.p, 2 * n * m, "contour: solve result");
-    // Q += (X - Y) diag(w/(z - l))  [feast.jl:68-70] ; nonlinear: Q0, Q1 [nlfeast.jl:56-58]
-    FEAST_TRY(launch_accumulate(ctx, n, m, ctx->X.p, ctx->W1.p, d_d, ctx->Q.p, nep ? ctx->Q1.p : nullptr, z, first_pass != 0));
+    int j0 = 0, mloc = m;
+    if (ctx->col_shard) {   // this rank's column slice of the right-hand side, as a compact block
+        j0 = (int)((int64_t)ctx->rank * m / ctx->nranks);
+        mloc = (int)((int64_t)(ctx->rank + 1) * m / ctx->nranks) - j0;
+        FEAST_TRY(launch_gather_cols(ctx, n, m, j0, mloc, rhs, ctx->W2.p));
+        rhs = ctx->W2.p;
+    }
+    ctx->m0 = mloc;          // the solvers size everything by ctx->m0: a compact n x mloc system
+    const int src = solve_shifted(ctx, solver, method, k, coef, rhs, ctx->W1.p, st, e1, rc_final);
+    ctx->m0 = m;
+    FEAST_TRY(src);
+    debug_check_finite(ctx, rhs, 2 * n * mloc, "contour: rhs");
+    debug_check_finite(ctx, ctx->W1.p, 2 * n * mloc, "contour: solve result");
+    // Q += (X - Y) diag(w/(z - l))  [feast.jl:68-70] ; nonlinear: Q0, Q1 [nlfeast.jl:56-58] ; moments S_p [beyn.jl:19-20,52-54]
+    c128* mp[FEAST_MAX_MOMENTS];
+    const int nmom = contour_nmom(ctx);
+    for (int p = 0; p < nmom; ++p) mp[p] = moment_block(ctx, p);
+    FEAST_TRY(launch_accumulate_slice(ctx, n, m, j0, mloc, ctx->X.p, ctx->W1.p, d_d, mp, nmom, z, first_pass != 0));
     cudaEventRecord(e2, ctx->stream);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // d (host vector) goes out of scope
     float a = 0, b = 0;
@@ -1252,9 +1383,10 @@ static int contour_end(feast_ctx* ctx, int solver, feast_stats& st) {
         cudaEvent_t e0 = ctx->evn[0], e3 = ctx->evn[3];
         const bool can_move_nodes = contour_can_move_nodes(ctx, solver);
         cudaEventRecord(e0, ctx->stream);
-        int rc = api->AllReduce(ctx->Q.p, ctx->Q.p, (size_t)2 * n * m, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
-        if (!rc && nep)
-            rc = api->AllReduce(ctx->Q1.p, ctx->Q1.p, (size_t)2 * n * m, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
+        (void)nep;
+        int rc = 0;
+        for (int p = 0; p < contour_nmom(ctx) && !rc; ++p)
+            rc = api->AllReduce(moment_block(ctx, p), moment_block(ctx, p), (size_t)2 * n * m, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
         if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclAllReduce: %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
         cudaEventRecord(e3, ctx->stream);
         if (can_move_nodes) {   // share the measured per-node costs (nnodes doubles) for the next pass
@@ -1294,7 +1426,7 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
     FEAST_TRY(contour_begin(ctx, solver));
     const int nnodes = (int)ctx->znodes.size();
     for (int k = 0; k < nnodes; ++k) {
-        if (ctx->owner[k] != ctx->rank) continue;
+        if (!ctx->col_shard && ctx->owner[k] != ctx->rank) continue;
         FEAST_TRY(contour_node(ctx, k, lambda, first_pass, solver, method, st, &rc_final));
     }
     FEAST_TRY(contour_end(ctx, solver, st));

@@ -81,6 +81,36 @@ __global__ void accumulate_kernel(int64_t total, int m, const c128* __restrict__
         if (Q1) Q1[t] = cadd(Q1[t], cmul(z, term));
     }
 }
+// column-slice / moment form: Y is a COMPACT n x mloc block holding the solutions of columns j0 .. j0+mloc-1;
+// Q_p[:, j0+jj] += z^p * term for p < nmom  (moment accumulators S_p = sum_k w_k z_k^p (...), src/beyn.jl:19-20,52-54)
+struct MomentPtrs { c128* q[FEAST_MAX_MOMENTS]; int nmom; };
+__global__ void accumulate_slice_kernel(int64_t n, int m, int j0, int mloc, const c128* __restrict__ X, const c128* __restrict__ Y,
+                                        const c128* __restrict__ d, MomentPtrs mp, c128 z, int first_pass) {
+    const int64_t total = n * mloc;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / mloc;
+        const int j = j0 + (int)(t - i * mloc);
+        const int64_t g = i * m + j;
+        const c128 dj = __ldg(d + j);
+        c128 term = first_pass ? cmul(__ldg(Y + t), dj) : cmul(csub(__ldg(X + g), __ldg(Y + t)), dj);
+#pragma unroll 1
+        for (int p = 0; p < mp.nmom; ++p) {
+            mp.q[p][g] = cadd(mp.q[p][g], term);
+            term = cmul(z, term);
+        }
+    }
+}
+// dst (compact n x mloc) = src[:, j0 : j0 + mloc] of a row-major n x m block
+__global__ void gather_cols_kernel(int64_t n, int m, int j0, int mloc, const c128* __restrict__ src, c128* __restrict__ dst) {
+    const int64_t total = n * mloc;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / mloc;
+        dst[t] = __ldg(src + i * m + j0 + (t - i * mloc));
+    }
+}
+__global__ void add_kernel(int64_t count, const c128* __restrict__ a, c128* __restrict__ y) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) y[t] = cadd(y[t], __ldg(a + t));
+}
 __global__ void conj_kernel(int64_t count, const c128* __restrict__ s, c128* __restrict__ d) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
         const c128 v = s[t];
@@ -236,6 +266,27 @@ int launch_accumulate(feast_ctx* ctx, int64_t n, int m, const c128* X, const c12
                       c128* Q1, hc128 z, bool first_pass) {
     accumulate_kernel<<<ew_grid(n * m), 256, 0, ctx->stream>>>(n * m, m, X, Y, d_d, Q, Q1, cmake(z.real(), z.imag()),
                                                               first_pass ? 1 : 0);
+    KLAUNCH_CHECK(ctx);
+    return 0;
+}
+int launch_accumulate_slice(feast_ctx* ctx, int64_t n, int m, int j0, int mloc, const c128* X, const c128* Y, const c128* d_d,
+                            c128* const* moments, int nmom, hc128 z, bool first_pass) {
+    if (nmom < 1 || nmom > FEAST_MAX_MOMENTS) return feast_fail(ctx, FEAST_ERR_STATE, "between 1 and %d moment accumulators", FEAST_MAX_MOMENTS);
+    MomentPtrs mp;
+    mp.nmom = nmom;
+    for (int p = 0; p < FEAST_MAX_MOMENTS; ++p) mp.q[p] = p < nmom ? moments[p] : nullptr;
+    accumulate_slice_kernel<<<ew_grid(n * mloc), 256, 0, ctx->stream>>>(n, m, j0, mloc, X, Y, d_d, mp, cmake(z.real(), z.imag()),
+                                                                       first_pass ? 1 : 0);
+    KLAUNCH_CHECK(ctx);
+    return 0;
+}
+int launch_axpy(feast_ctx* ctx, int64_t count, const c128* a, c128* y) {   // y += a
+    add_kernel<<<ew_grid(count), 256, 0, ctx->stream>>>(count, a, y);
+    KLAUNCH_CHECK(ctx);
+    return 0;
+}
+int launch_gather_cols(feast_ctx* ctx, int64_t n, int m, int j0, int mloc, const c128* src, c128* dst) {
+    gather_cols_kernel<<<ew_grid(n * mloc), 256, 0, ctx->stream>>>(n, m, j0, mloc, src, dst);
     KLAUNCH_CHECK(ctx);
     return 0;
 }

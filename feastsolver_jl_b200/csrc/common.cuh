@@ -170,6 +170,11 @@ struct feast_ctx {
     // subspace blocks
     int m0 = 0;
     BlockVec Q, X, R, Q1, W1, W2;       // Q1: second moment accumulator (polynomial)
+    std::vector<BlockVec> mom;          // moment accumulators S_2, S_3, ... (S_0 = Q, S_1 = Q1)
+    int nmom = 0;                       // requested number of moments (0: default of the problem kind)
+    std::vector<double> last_fro;       // ||T(l_j)||_F of the last polynomial residual
+    int shard_mode = FEAST_SHARD_AUTO;  // multi-GPU sharding axis of the contour loop
+    bool col_shard = false;             // the running pass shards right-hand-side columns instead of nodes
     BlockVec Ql, Xl, Rl;                // left subspace of the two-sided driver (dual_gen_feast!)
     BlockVec kx, kr, kp, kq, ks, kt, kv, krh; // Krylov work
     c128* gm_V = nullptr;         // GMRES basis: (gm_restart + 1) blocks

@@ -45,6 +45,13 @@ int launch_residual_combine(feast_ctx* ctx, int64_t n, int m, c128* AX_inout_R, 
 // first_pass: term = Y * w (nlfeast.jl:39-45, d[j] = w for all j)
 int launch_accumulate(feast_ctx* ctx, int64_t n, int m, const c128* X, const c128* Y, const c128* d_d,
                       c128* Q, c128* Q1, hc128 z, bool first_pass);
+// Column-slice / moment form of the accumulation: Y is a compact n x mloc block (solutions of columns j0 .. j0+mloc-1),
+// moments[p][:, j0+jj] += z^p * term for p < nmom.
+int launch_accumulate_slice(feast_ctx* ctx, int64_t n, int m, int j0, int mloc, const c128* X, const c128* Y, const c128* d_d,
+                            c128* const* moments, int nmom, hc128 z, bool first_pass);
+int launch_axpy(feast_ctx* ctx, int64_t count, const c128* a, c128* y);   // y += a
+// dst (compact n x mloc) = src[:, j0 : j0 + mloc]
+int launch_gather_cols(feast_ctx* ctx, int64_t n, int m, int j0, int mloc, const c128* src, c128* dst);
 // layout conversion between host column-major (ld) and device row-major blocks
 // perm (device, new -> old row map, may be nullptr): device row i holds host row perm[i]
 int launch_colmajor_to_rowmajor(feast_ctx* ctx, int64_t n, int m, const c128* src, int64_t ld, c128* dst, const int* perm = nullptr);

@@ -107,9 +107,12 @@ class FeastContext:
         w = np.ascontiguousarray(weights, dtype=np.complex128)
         self._ck(self.lib.feast_set_contour(self.h, len(z), _lib.ptr(z), _lib.ptr(w)))
 
-    def set_solver(self, kind=_lib.SOLVER_AUTO, krylov=_lib.KRYLOV_AUTO, inner_tol=1e-8, max_inner=4000, store=False, precond=None):
+    def set_solver(self, kind=_lib.SOLVER_AUTO, krylov=_lib.KRYLOV_AUTO, inner_tol=1e-8, max_inner=4000, store=False, precond=None,
+                   shard=None):
         if precond is not None:   # before set_solver: one layout rebuild at most
             self.set_preconditioner(precond)
+        if shard is not None:
+            self.set_sharding(shard)
         self._ck(self.lib.feast_set_solver(self.h, kind, krylov, float(inner_tol), int(max_inner), int(bool(store))))
 
     def set_preconditioner(self, kind=_lib.PRECOND_AUTO):
@@ -149,6 +152,11 @@ class FeastContext:
         self._ck(self.lib.feast_set_subspace(self.h, n, m0, _lib.ptr(Xf), n))
         self.m0 = m0
 
+    def set_X(self, X):
+        """Overwrite the device block X only (Q / moment accumulators untouched)."""
+        Xf = _lib.as_f_c128(X)
+        self._ck(self.lib.feast_set_X(self.h, _lib.ptr(Xf), Xf.shape[0]))
+
     def _get(self, fn):
         out = np.empty((self.n, self.m0), dtype=np.complex128, order="F")
         self._ck(fn(self.h, _lib.ptr(out), self.n))
@@ -172,11 +180,40 @@ class FeastContext:
         return Aq, Bq
 
     def recover_residual(self, Xq, lam):
-        Xq = np.asfortranarray(Xq, dtype=np.complex128)
+        """X = Q Xq (Xq None: X as it is), x_j /= ||x_j||, residual vectors and norms."""
+        Xq_p = None
+        if Xq is not None:
+            Xq = np.asfortranarray(Xq, dtype=np.complex128)
+            Xq_p = _lib.ptr(Xq)
         lam = np.ascontiguousarray(lam, dtype=np.complex128)
         res = np.empty(self.m0, np.float64)
-        self._ck(self.lib.feast_recover_residual(self.h, _lib.ptr(Xq), _lib.ptr(lam), _lib.ptr(res)))
+        self._ck(self.lib.feast_recover_residual(self.h, Xq_p, _lib.ptr(lam), _lib.ptr(res)))
         return res
+
+    def last_fro(self):
+        fro = np.empty(self.m0, np.float64)
+        self._ck(self.lib.feast_last_fro(self.h, _lib.ptr(fro)))
+        return fro
+
+    def set_sharding(self, mode=_lib.SHARD_AUTO):
+        self._ck(self.lib.feast_set_sharding(self.h, int(mode)))
+
+    # -- moments (beyn / block_SS! / nlfeast_moments!)
+    def set_moments(self, nmom):
+        self._ck(self.lib.feast_set_moments(self.h, int(nmom)))
+
+    def block_gram(self, a, b):
+        """block(a)^H block(b); ids: p >= 0 moment S_p, -1 X, -2 R."""
+        G = np.empty((self.m0, self.m0), np.complex128, order="F")
+        self._ck(self.lib.feast_block_gram(self.h, int(a), int(b), _lib.ptr(G)))
+        return G
+
+    def moment_combine(self, W):
+        """X = sum_p S_p W[p*m0:(p+1)*m0, :]."""
+        W = np.asfortranarray(W, dtype=np.complex128)
+        nblk = W.shape[0] // self.m0
+        assert W.shape == (nblk * self.m0, self.m0)
+        self._ck(self.lib.feast_moment_combine(self.h, nblk, _lib.ptr(W), W.shape[0]))
 
     def contour_apply(self, lam, first_pass=False):
         st = FeastStats()
@@ -588,6 +625,269 @@ def nlfeast(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=1
         if own_ctx:
             ctx.close()
     return Lam, X, res
+
+
+class _NepSession:
+    """Shared plumbing of the moment-based nonlinear drivers: a context holding T (polynomial coefficients on the
+    device, or a host-evaluated closure through the sampled-operator entries), one contour pass with `nmom` moment
+    accumulators, and the residuals of the current block X."""
+
+    def __init__(self, T, X, nodes, c, r, store, solver_opts, comm, ctx=None):
+        self.sampled = callable(T)
+        self.T = T
+        N, m0 = X.shape
+        self.N, self.m0, self.nodes = N, m0, nodes
+        self.own = ctx is None
+        self.ctx = FeastContext() if ctx is None else ctx
+        self.contour = circular_contour_trapezoidal(c, r, nodes)      # theta = LinRange(pi/nodes, 2pi - pi/nodes, nodes)
+        ctx = self.ctx
+        if self.sampled:
+            T0 = T(self.contour.nodes[0])
+            if T0.shape != (N, N):
+                raise ValueError("Incorrect dimensions of X, must match T")
+            ctx.set_operator(0, T0, n=N)
+            ctx.set_problem(_lib.PROBLEM_SAMPLED, 1, N)
+        else:
+            coeffs = list(T)
+            if any(sp.issparse(a) for a in coeffs) and not all(sp.issparse(a) for a in coeffs):
+                coeffs = [a.toarray() if sp.issparse(a) else np.asarray(a) for a in coeffs]
+            for i, Ai in enumerate(coeffs):
+                ctx.set_operator(i, Ai, n=N)
+            ctx.set_problem(_lib.PROBLEM_POLYNOMIAL, len(coeffs), N)
+        if comm is not None:
+            comm(ctx)
+        ctx.set_contour(self.contour.nodes, self.contour.weights)
+        self.owners = node_owners(self.contour.nodes, ctx.nranks) if ctx.nranks > 1 else [0] * nodes
+        if ctx.nranks > 1:
+            ctx.set_node_owners(self.owners)
+        ctx.set_solver(store=store, **(solver_opts or {}))
+        ctx.set_subspace(X)
+
+    def contour_pass(self, nmom, Lam=None):
+        ctx = self.ctx
+        ctx.set_moments(nmom)
+        first = Lam is None
+        if not self.sampled:
+            return ctx.contour_apply(Lam, first_pass=first)
+        mine = [k for k in range(self.nodes) if self.owners[k] == ctx.rank] or [-1]
+        st = None
+        for i, k in enumerate(mine):
+            if k >= 0 and ctx.node_needs_sample(k):
+                ctx.set_sample(self.T(self.contour.nodes[k]))
+            st = ctx.contour_node(k, Lam, first, (1 if i == 0 else 0) | (2 if i == len(mine) - 1 else 0))
+        return st
+
+    def residuals(self, Lam, Xq=None):
+        """x_j /= ||x_j||, R_j = T(l_j) x_j; returns (relative residuals, ||T(l_j)||_F)."""
+        ctx = self.ctx
+        res = ctx.recover_residual(Xq, Lam)
+        if not self.sampled:
+            return res, ctx.last_fro()
+        fro = np.empty(self.m0)
+        for j in range(self.m0):
+            Tj = self.T(Lam[j])
+            ctx.set_sample(Tj)
+            fro[j] = spla_norm(Tj) if sp.issparse(Tj) else float(np.linalg.norm(Tj))
+            res[j] = ctx.sampled_residual(j, fro[j])
+        return res, fro
+
+    def close(self):
+        self.ctx.set_moments(0)
+        if self.own:
+            self.ctx.close()
+
+
+def _beyn_small(Rf, G1):
+    """m0 x m0 part of beyn_svd_step! (src/utils.jl:70-75) given Q0 = U Rf and G1 = U' Q1."""
+    U, S, Vh = sla.svd(Rf, check_finite=False)
+    Am = (U.conj().T @ G1) @ Vh.conj().T * (1.0 / S)[None, :]
+    w, v = sla.eig(Am, check_finite=False)
+    p = np.lexsort((w.imag, w.real))
+    return np.ascontiguousarray(w[p]), U @ v[:, p]
+
+
+def beyn(T, A, X, nodes, *, c=complex(0.0, 0.0), r=1.0, ctx=None, solver_opts=None, comm=None):
+    """beyn(T, A, X, nodes; c, r)  (src/beyn.jl:2-34): Beyn's integral method -- ONE contour pass with the two moments
+    Q0, Q1, the Beyn reduction, ABSOLUTE residuals ||T(l) x||, everything sorted by residual.  `A` only supplies the
+    dimensions, X is not modified.  T: polynomial coefficient list (device assembly) or a callable (host samples).
+    (Upstream weights Q0/Q1 by exp(i theta)/nodes without the factor r, beyn.jl:19-20; r cancels in U' Q1 V S^-1.)"""
+    N, m0 = X.shape
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("Incorrect dimensions of A, must be square")          # beyn.jl:5-6
+    if A.shape[0] != N:
+        raise ValueError("Incorrect dimensions of X0, must match A")           # beyn.jl:7-8
+    ses = _NepSession(T, np.asarray(X, dtype=np.complex128), nodes, c, r, False, solver_opts, comm, ctx)
+    try:
+        ses.contour_pass(2)                                                    # beyn.jl:16-21
+        Rf, G1 = ses.ctx.beyn_reduce()                                         # tall part of svd!(Q0), U' Q1
+        Lam, Xq = _beyn_small(Rf, G1)                                          # beyn.jl:22-25
+        res, fro = ses.residuals(Lam, Xq)
+        Xn = ses.ctx.get_X()
+    finally:
+        ses.close()
+    res = res * fro                                                            # beyn.jl:28: no normalisation by ||T||
+    p = np.argsort(res, kind="stable")
+    return Lam[p], Xn[:, p], res[p]
+
+
+def block_SS(T, X, nodes=16, moments=2, *, c=complex(0.0, 0.0), r=1.0, debug=False, Y=None, seed=0, ctx=None,
+             solver_opts=None, comm=None):
+    """block_SS!(T, X, nodes=2^4, moments=2; c, r)  (src/beyn.jl:36-94): block Sakurai-Sugiura.  2*moments+1 moment
+    accumulators S_p in one contour pass (the p-loop of the accumulate kernel), Hankel blocks Y' S_p as m0 x m0 Grams on
+    the device, the small SVD / generalized eigenproblem on the host, X = [S_0 .. S_{moments-1}] V Xq back on the device.
+    Upstream draws the probe Y = rand(ComplexF64, N, m0) unseeded; pass `Y` (or `seed`) for reproducibility."""
+    N, m0 = X.shape
+    K = moments * m0
+    if 2 * moments + 1 > _lib.MAX_MOMENTS:
+        raise ValueError(f"moments <= {(_lib.MAX_MOMENTS - 1) // 2}")
+    if Y is None:
+        rng = np.random.default_rng(seed)
+        Y = rng.random((N, m0)) + 1j * rng.random((N, m0))
+    ses = _NepSession(T, np.asarray(X, dtype=np.complex128), nodes, c, r, False, solver_opts, comm, ctx)
+    try:
+        cx = ses.ctx
+        cx.orthonormalize_X()                                                  # X = Matrix(qr(X).Q)      beyn.jl:41
+        ses.contour_pass(2 * moments + 1)                                      # beyn.jl:50-56
+        cx.set_X(Y)                                                            # the probe takes the X block: Grams Y' S_p
+        G = [cx.block_gram(-1, p) for p in range(2 * moments + 1)]
+        Q0 = np.zeros((m0 * moments, K), complex)
+        Q1 = np.zeros((m0 * moments, K), complex)
+        for i in range(1, moments + 1):
+            for j in range(1, moments + 1):
+                Q0[(i - 1) * m0:i * m0, (j - 1) * m0:j * m0] = G[i + j - 1]     # beyn.jl:66
+                Q1[(i - 1) * m0:i * m0, (j - 1) * m0:j * m0] = G[i + j]         # beyn.jl:67
+        U, sv, Vh = sla.svd(Q0, check_finite=False)
+        n = min(int(np.count_nonzero(sv / sv[0] > 1e-13)), K)                   # beyn.jl:78
+        V = Vh.conj().T
+        H1 = U[:, :n].conj().T @ Q1 @ V[:, :n]
+        H0 = U[:, :n].conj().T @ Q0 @ V[:, :n]
+        Lam, Xq = sla.eig(H1, H0, check_finite=False)                           # beyn.jl:83
+        W = V[:, :n] @ Xq                                                       # X = S[:, 1:K] * V * Xq    beyn.jl:87
+        Xn = np.empty((N, n), np.complex128, order="F")
+        res = np.empty(n)
+        for c0 in range(0, n, m0):                                              # the device block is m0 wide
+            c1 = min(n, c0 + m0)
+            Wc = np.zeros((K, m0), complex)
+            Wc[:, :c1 - c0] = W[:, c0:c1]
+            lam_c = np.full(m0, Lam[c0], complex)
+            lam_c[:c1 - c0] = Lam[c0:c1]
+            if c1 - c0 < m0:
+                Wc[:, c1 - c0:] = W[:, [c0]]                                    # pad with a copy (no zero columns to normalise)
+            cx.moment_combine(Wc)
+            rc, _ = ses.residuals(lam_c)                                        # normalise, relative residuals beyn.jl:90-93
+            Xn[:, c0:c1] = cx.get_X()[:, :c1 - c0]
+            res[c0:c1] = rc[:c1 - c0]
+    finally:
+        ses.close()
+    return Lam, Xn, res
+
+
+def nlfeast_moments(T, X, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=10e-12, moments=2, store=True,
+                    spurious=1e-5, ctx=None, solver_opts=None, comm=None, stats=None):
+    """nlfeast_moments!(T, X, nodes, iter; ...)  (src/nlfeast.jl:173-318): nlfeast with 2*moments moment accumulators and a
+    moments*m0-dimensional Beyn reduction of the block-Hankel matrices per pass.  Returns (L, Y, res) with moments*m0
+    entries sorted by residual; X is overwritten by the m0 best unit-norm vectors.
+
+    Device form of the tall SVD of Q0 (moments*N x moments*m0): its Gram matrix and Q0' Q1 are sums of the m0 x m0 Grams
+    S_a' S_b of the moment blocks, Q0 = U S V' follows from the Hermitian eigendecomposition of the Gram matrix, and
+    Y = U[1:N, :] vecs = [S_0 .. S_{moments-1}] V S^-1 vecs is one combination of moment blocks.  Directions whose
+    singular value is below 1e-7 of the largest carry no information in this form (the Gram matrix squares the
+    condition number) and are dropped; upstream divides by them (nlfeast.jl:224), which only produces spurious pairs."""
+    N, m0 = X.shape
+    M = moments
+    if 2 * M > _lib.MAX_MOMENTS:
+        raise ValueError(f"moments <= {_lib.MAX_MOMENTS // 2}")
+    ses = _NepSession(T, X, nodes, c, r, store, solver_opts, comm, ctx)
+    hist = []
+    try:
+        cx = ses.ctx
+        K = M * m0
+
+        def reduce_and_residuals():
+            G = {(a, b): cx.block_gram(a, b) for a in range(2 * M - 1) for b in range(a, 2 * M)}
+
+            def gram(a, b):
+                return G[(a, b)] if a <= b else G[(b, a)].conj().T
+            G0 = np.zeros((K, K), complex)
+            G01 = np.zeros((K, K), complex)
+            for j in range(M):
+                for jp in range(M):
+                    G0[j * m0:(j + 1) * m0, jp * m0:(jp + 1) * m0] = sum(gram(i + j, i + jp) for i in range(M))
+                    G01[j * m0:(j + 1) * m0, jp * m0:(jp + 1) * m0] = sum(gram(i + j, i + jp + 1) for i in range(M))
+            ev, V = np.linalg.eigh((G0 + G0.conj().T) / 2)
+            ev, V = ev[::-1], V[:, ::-1]
+            keep = ev > (1e-7 ** 2) * ev[0]
+            sv = np.sqrt(ev[keep])
+            V = V[:, keep]
+            Am = (V.conj().T @ G01 @ V) / sv[:, None] / sv[None, :]               # S^-1 V' Q0' Q1 V S^-1    nlfeast.jl:222-224
+            w, v = sla.eig(Am, check_finite=False)
+            p = np.lexsort((w.imag, w.real))
+            w, v = w[p], v[:, p]
+            W = (V / sv[None, :]) @ v                                             # Y = [S_0 .. S_{M-1}] W       nlfeast.jl:226
+            nk = w.size
+            Lam_all, res_all = np.empty(nk, complex), np.empty(nk)
+            for c0 in range(0, nk, m0):
+                c1 = min(nk, c0 + m0)
+                Wc = np.zeros((K, m0), complex)
+                Wc[:, :c1 - c0] = W[:, c0:c1]
+                lam_c = np.full(m0, w[c0], complex)
+                lam_c[:c1 - c0] = w[c0:c1]
+                if c1 - c0 < m0:
+                    Wc[:, c1 - c0:] = W[:, [c0]]
+                cx.moment_combine(Wc)
+                rc, _ = ses.residuals(lam_c)                                      # update_R_moments!, utils.jl:118-123
+                Lam_all[c0:c1], res_all[c0:c1] = w[c0:c1], rc[:c1 - c0]
+            p = np.argsort(res_all, kind="stable")                                # utils.jl:125-133
+            Lam_all, res_all, W = Lam_all[p], res_all[p], W[:, p]
+            # X = Y[:, 1:m0] with its residual vectors R (the right-hand side of the next pass)
+            Wc = np.zeros((K, m0), complex)
+            nb = min(m0, nk)
+            Wc[:, :nb] = W[:, :nb]
+            lam_c = np.full(m0, Lam_all[0], complex)
+            lam_c[:nb] = Lam_all[:nb]
+            if nb < m0:
+                Wc[:, nb:] = W[:, [0]]
+            cx.moment_combine(Wc)
+            ses.residuals(lam_c)
+            return Lam_all, res_all, W, lam_c
+
+        ses.contour_pass(2 * M)                                                   # nlfeast.jl:195-213
+        Lam, res, W, lam_x = reduce_and_residuals()
+        hist.append({"nit": 0})
+        for nit in range(1, iter + 1):
+            ses.contour_pass(2 * M, Lam=lam_x)                                    # nlfeast.jl:255-275
+            Lam, res, W, lam_x = reduce_and_residuals()
+            nb = min(m0, Lam.size)
+            inside = in_contour(Lam[:nb], c, r)
+            res_inside = res[:nb][inside]
+            hist.append({"nit": nit, "inside": int(inside.sum()),
+                         "max_res_inside": float(res_inside.max()) if inside.any() else float("nan")})
+            if debug:
+                iter_debug_print(nit, Lam[:nb], res[:nb], CircularContour(c, r, None, None), spurious)
+            if res_inside.size > 0 and res_inside.max() < eps:                    # nlfeast.jl:297
+                break
+            good = res_inside[res_inside < spurious]
+            if nit > 1 and good.size > 0 and good.max() < eps:                    # nlfeast.jl:300
+                break
+        X[:, :] = cx.get_X()
+        # all moments*m0 vectors, in residual order
+        Yall = np.empty((N, Lam.size), np.complex128, order="F")
+        for c0 in range(0, Lam.size, m0):
+            c1 = min(Lam.size, c0 + m0)
+            Wc = np.zeros((K, m0), complex)
+            Wc[:, :c1 - c0] = W[:, c0:c1]
+            if c1 - c0 < m0:
+                Wc[:, c1 - c0:] = W[:, [c0]]
+            cx.moment_combine(Wc)
+            lam_c = np.full(m0, Lam[c0], complex)
+            lam_c[:c1 - c0] = Lam[c0:c1]
+            ses.residuals(lam_c)
+            Yall[:, c0:c1] = cx.get_X()[:, :c1 - c0]
+        if stats is not None:
+            stats["history"] = hist
+    finally:
+        ses.close()
+    return Lam, Yall, res
 
 
 def ifeast(A, X0, nodes, iter, *, c=complex(0.0, 0.0), r=1.0, debug=False, eps=0.05, ctx=None, solver_opts=None, stats=None):

@@ -40,3 +40,9 @@ def node_owners(nodes, nranks, costs=None):
 
 def local_nodes(owner, rank):
     return [k for k, o in enumerate(owner) if o == rank]
+
+
+def column_slice(m0, nranks, rank):
+    """Columns [j0, j1) of every node's right-hand side that `rank` solves when the contour loop shards COLUMNS
+    (Krylov inner solves; csrc/api.cu contour_node): j0 = floor(rank m0 / nranks), j1 = floor((rank + 1) m0 / nranks)."""
+    return (rank * m0) // nranks, ((rank + 1) * m0) // nranks

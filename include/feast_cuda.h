@@ -70,6 +70,11 @@ enum { FEAST_PROBLEM_STANDARD = 0,    /* A x = l x          feast!      src/feas
 /* Preconditioner of the Krylov inner solves: a smoothed-aggregation multigrid V-cycle built from the real symmetric
  * operator slots (linear problems, COCG).  AUTO = use it when applicable and n is large enough to pay for the setup. */
 enum { FEAST_PRECOND_NONE = 0, FEAST_PRECOND_AMG = 1, FEAST_PRECOND_AUTO = 2 };
+/* multi-GPU sharding axis of the contour loop: nodes (src/feast.jl:34 threads over them), or the columns of every
+ * node's right-hand side (Krylov inner solves only: no factorisation to keep together, perfect balance); AUTO picks
+ * columns for Krylov solves and nodes for the direct solvers */
+enum { FEAST_SHARD_AUTO = 0, FEAST_SHARD_NODES = 1, FEAST_SHARD_COLUMNS = 2 };
+#define FEAST_MAX_MOMENTS 8          /* moment accumulators S_p = sum_k w_k z_k^p (...) of one contour pass */
 #define FEAST_MAX_SLOTS 8            /* slot 0 = A (or A_0), 1 = B (or A_1), ... A_7 */
 
 typedef struct {
@@ -85,7 +90,7 @@ typedef struct {
     double t_spmm_ms;         /* Krylov: device time inside the SpMM launches       */
     int64_t spmm_launches;    /* Krylov: number of SpMM launches                    */
     int    precond_levels;    /* levels of the multigrid preconditioner in use (0: unpreconditioned) */
-    int    reserved0;
+    int    col_sharded;       /* 1: this pass sharded right-hand-side COLUMNS over the ranks (every rank ran all nodes) */
 } feast_stats;
 
 /* ---- library / context ---------------------------------------------- */
@@ -134,6 +139,7 @@ FEAST_API int  feast_set_node_owners(feast_ctx* ctx, int nnodes, const int* owne
 /* ---- subspace --------------------------------------------------------- */
 /* Upload X0 (n x m0 column-major, ldx >= n): becomes Q (and X).  src/feast.jl:21 */
 FEAST_API int  feast_set_subspace(feast_ctx* ctx, int64_t n, int m0, const feast_c128* X, int64_t ldx);
+FEAST_API int  feast_set_X(feast_ctx* ctx, const feast_c128* X, int64_t ldx); /* overwrite the block X only */
 FEAST_API int  feast_get_X(feast_ctx* ctx, feast_c128* X, int64_t ldx);   /* normalised Ritz vectors */
 FEAST_API int  feast_get_Q(feast_ctx* ctx, feast_c128* Q, int64_t ldq);   /* current basis / accumulator */
 FEAST_API int  feast_get_R(feast_ctx* ctx, feast_c128* R, int64_t ldr);   /* residual vectors */
@@ -146,6 +152,7 @@ FEAST_API int  feast_project(feast_ctx* ctx, feast_c128* Aq, feast_c128* Bq);
 /* X = Q Xq; x_j /= ||x_j||; R_j = (A - l_j B) x_j (or T(l_j) x_j); res_j = ||R_j||
  * (absolute; polynomial: relative to ||T(l_j)||_F).  Replaces src/feast.jl:48-50,
  * :125-127, src/utils.jl:104-116,151-157,166-171.                             */
+/* Xq may be NULL: X is then taken as it is (normalised in place), e.g. after feast_moment_combine */
 FEAST_API int  feast_recover_residual(feast_ctx* ctx, const feast_c128* Xq, const feast_c128* lambda, double* res);
 /* The hot loop.  Linear: Q = sum_k (X - (A - z_k B)^-1 R) diag(w_k/(z_k - l_j))
  * (src/feast.jl:57-71, :134-147).  Polynomial: Q0, Q1 of src/nlfeast.jl:36-61;
@@ -166,6 +173,12 @@ FEAST_API int  feast_set_sample_csc(feast_ctx* ctx, int64_t n, const int64_t* co
 FEAST_API int  feast_contour_node(feast_ctx* ctx, int k, const feast_c128* lambda, int first_pass, int phase, feast_stats* stats);
 FEAST_API int  feast_node_needs_sample(const feast_ctx* ctx, int k);   /* 0 when a stored factorisation of node k exists */
 FEAST_API int  feast_sampled_residual(feast_ctx* ctx, int j, double fro, double* res);
+FEAST_API int  feast_set_sharding(feast_ctx* ctx, int mode);                 /* FEAST_SHARD_* */
+/* moment machinery of the one-shot contour solvers (src/beyn.jl:2-94) and nlfeast_moments! (src/nlfeast.jl:173-318) */
+FEAST_API int  feast_set_moments(feast_ctx* ctx, int nmom);
+FEAST_API int  feast_block_gram(feast_ctx* ctx, int a, int b, feast_c128* G); /* ids: p >= 0 moment S_p, -1 X, -2 R */
+FEAST_API int  feast_moment_combine(feast_ctx* ctx, int nblk, const feast_c128* W, int64_t ldw);
+FEAST_API int  feast_last_fro(feast_ctx* ctx, double* fro);
 FEAST_API int  feast_beyn_reduce(feast_ctx* ctx, feast_c128* Rf, feast_c128* G1);
 /* contour_estimate_eig (src/stochastic.jl:2-33): with the probe vectors uploaded by
  * feast_set_subspace, est = Re sum_k w_k tr(X' (z_k B - A)^-1 X) / m0 (node-sharded).   */

@@ -242,12 +242,14 @@ class Timers(dict):
 # --------------------------------------------------------------------------
 
 def _feast_core(X, A, B, contour, iter, eps, store, factorizer, left_divider,
-                timers=None, history=None, node_subset=None, reduce_fn=None):
+                timers=None, history=None, node_subset=None, reduce_fn=None, col_slice=None):
     """Shared skeleton of feast! (src/feast.jl:10-80) and gen_feast!
     (src/feast.jl:89-156).  B=None is the standard problem (B = I).
 
     `node_subset` / `reduce_fn` exist so tests can emulate node sharding over
-    ranks (each rank accumulates its nodes, then reduce_fn sums Q across ranks).
+    ranks (each rank accumulates its nodes, then reduce_fn sums Q across ranks);
+    `col_slice` = (j0, j1) emulates the column sharding of the device Krylov path
+    (a rank runs ALL nodes on the right-hand-side columns j0 .. j1-1 only).
     """
     N, m0 = X.shape
     if A.shape[0] != A.shape[1]:
@@ -326,6 +328,9 @@ def _feast_core(X, A, B, contour, iter, eps, store, factorizer, left_divider,
                 t0 = time.perf_counter()
                 temp = X - temp  # feast.jl:68
                 temp *= (resolvent * contour.weights[i])[None, :]  # feast.jl:69
+                if col_slice is not None:   # the other columns belong to other ranks
+                    temp[:, :col_slice[0]] = 0.0
+                    temp[:, col_slice[1]:] = 0.0
                 Q += temp  # feast.jl:70
                 tm.add("accumulate", t0)
             if reduce_fn is not None:
@@ -503,6 +508,135 @@ def nlfeast(T, X, nodes, iter, *, c=0.0 + 0.0j, r=1.0, eps=10e-12, store=True,
             break
     normalize_cols(X)  # nlfeast.jl:82
     return Lam, X, res
+
+
+# --------------------------------------------------------------------------
+# one-shot contour solvers and higher moments  (src/beyn.jl, src/nlfeast.jl:173-318)
+# --------------------------------------------------------------------------
+
+def beyn(T, A, X, nodes, *, c=0.0 + 0.0j, r=1.0):
+    """beyn(T, A, X, nodes; c, r)  (src/beyn.jl:2-34): Beyn's integral method, one contour pass, two moments.
+    A only supplies the dimensions (:5-9).  Weights exp(i theta)/nodes (no factor r, :19-20: it cancels in
+    U' Q1 V S^-1).  Returns (L[p], X[:, p], res[p]) sorted by the ABSOLUTE residual ||T(l) x|| (:29-33)."""
+    N, m0 = X.shape
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("Incorrect dimensions of A, must be square")
+    if A.shape[0] != N:
+        raise ValueError("Incorrect dimensions of X0, must match A")
+    theta = np.linspace(np.pi / nodes, 2 * np.pi - np.pi / nodes, nodes)
+    Q0 = np.zeros((N, m0), complex)
+    Q1 = np.zeros((N, m0), complex)
+    for th in theta:
+        z = r * np.exp(1j * th) + c
+        temp = left_divide(lu_factorizer(T(z)), X)
+        Q0 += temp * (np.exp(1j * th) / nodes)
+        Q1 += temp * (z * np.exp(1j * th) / nodes)
+    Lam, Xn = beyn_svd_step(Q0, Q1)
+    res = np.array([np.linalg.norm(T(Lam[i]) @ Xn[:, i]) for i in range(m0)])
+    p = np.argsort(res, kind="stable")
+    return Lam[p], Xn[:, p], res[p]
+
+
+def contour_moments(T, X, nodes, nmom, c, r, rhs=None, Lam=None):
+    """S_p = sum_k z_k^p (T(z_k)^-1 X) w_k, w_k = r exp(i theta_k)/nodes  (src/beyn.jl:50-56, src/nlfeast.jl:195-213);
+    with rhs/Lam given: the residual-inverse-iteration form (X - T(z_k)^-1 R) diag(w_k/(z_k - lam))  (nlfeast.jl:255-275)."""
+    N, m0 = X.shape
+    theta = np.linspace(np.pi / nodes, 2 * np.pi - np.pi / nodes, nodes)
+    S = [np.zeros((N, m0), complex) for _ in range(nmom)]
+    for th in theta:
+        z = r * np.exp(1j * th) + c
+        w = r * np.exp(1j * th) / nodes
+        F = lu_factorizer(T(z))
+        if rhs is None:
+            temp = left_divide(F, X) * w
+        else:
+            temp = (X - left_divide(F, rhs)) * ((1.0 / (z - Lam)) * w)[None, :]
+        for p in range(nmom):
+            S[p] += temp * z ** p
+    return S
+
+
+def block_SS(T, X, nodes=16, moments=2, *, c=0.0 + 0.0j, r=1.0, Y=None, rng=None):
+    """block_SS!(T, X, nodes, moments; c, r)  (src/beyn.jl:36-94): block Sakurai-Sugiura with a probe block Y
+    (upstream: rand(ComplexF64, N, m0), unseeded -- pass Y for reproducibility).  Returns (L, X, res) with
+    n <= moments*m0 entries (numerical rank of the Hankel matrix at 1e-13, :78), res relative (:92)."""
+    N, m0 = X.shape
+    K = moments * m0
+    Xo, _ = np.linalg.qr(X)
+    if Y is None:
+        rng = np.random.default_rng(0) if rng is None else rng
+        Y = rng.random((N, m0)) + 1j * rng.random((N, m0))
+    l = Y.shape[1]
+    S = contour_moments(T, Xo, nodes, 2 * moments + 1, c, r)
+    Q0 = np.zeros((l * moments, K), complex)
+    Q1 = np.zeros((l * moments, K), complex)
+    for i in range(1, moments + 1):
+        for j in range(1, moments + 1):
+            Q0[(i - 1) * l:i * l, (j - 1) * m0:j * m0] = Y.conj().T @ S[i + j - 1]     # :66
+            Q1[(i - 1) * l:i * l, (j - 1) * m0:j * m0] = Y.conj().T @ S[i + j]         # :67
+    U, sv, Vh = sla.svd(Q0, full_matrices=False, check_finite=False)
+    n = min(int(np.count_nonzero(sv / sv[0] > 1e-13)), K)
+    V = Vh.conj().T
+    H1 = U[:, :n].conj().T @ Q1 @ V[:, :n]
+    H0 = U[:, :n].conj().T @ Q0 @ V[:, :n]
+    Lam, Xq = sla.eig(H1, H0, check_finite=False)
+    Xn = np.hstack(S[:moments]) @ V[:, :n] @ Xq                                        # :87
+    Xn /= np.linalg.norm(Xn, axis=0)
+    res = np.array([np.linalg.norm(T(Lam[i]) @ Xn[:, i]) / _fro(T(Lam[i])) for i in range(n)])
+    return Lam, Xn, res
+
+
+def _moments_reduce(S, moments, N, m0):
+    """Block-Hankel Q0, Q1 (moments*N x moments*m0) from S_0 .. S_{2 moments - 1}, tall SVD, A = U' Q1 V S^-1, eig,
+    Y = U[1:N, :] vecs  (src/nlfeast.jl:216-231)."""
+    K = moments * m0
+    Q0 = np.zeros((moments * N, K), complex)
+    Q1 = np.zeros((moments * N, K), complex)
+    for i in range(1, moments + 1):
+        for j in range(1, moments + 1):
+            Q0[(i - 1) * N:i * N, (j - 1) * m0:j * m0] = S[i + j - 2]
+            Q1[(i - 1) * N:i * N, (j - 1) * m0:j * m0] = S[i + j - 1]
+    U, sv, Vh = sla.svd(Q0, full_matrices=False, check_finite=False)
+    Am = (U.conj().T @ Q1) @ Vh.conj().T * (1.0 / sv)[None, :]
+    w, v = sla.eig(Am, check_finite=False)
+    w, v = _julia_eig_sort(w, v)
+    return w, U[:N, :] @ v
+
+
+def _update_R_moments(Y, Lam, T):
+    """src/utils.jl:118-134: normalise, R_i = T(l_i) y_i, relative residuals, everything sorted by residual."""
+    R = update_R_nep(Y, Lam, T)
+    res = residuals_nep(R, Lam, T)
+    p = np.argsort(res, kind="stable")
+    return Y[:, p], R[:, p], Lam[p], res[p]
+
+
+def nlfeast_moments(T, X, nodes, iter, *, c=0.0 + 0.0j, r=1.0, eps=10e-12, moments=2, store=True, spurious=1e-5,
+                    history=None):
+    """nlfeast_moments!(T, X, nodes, iter; ...)  (src/nlfeast.jl:173-318): nlfeast with 2*moments moment accumulators and
+    a moments*m0-dimensional Beyn reduction per pass.  Returns (L, Y, res) with moments*m0 entries sorted by residual;
+    X is overwritten by the m0 best (unit-norm) vectors."""
+    N, m0 = X.shape
+    S = contour_moments(T, X, nodes, 2 * moments, c, r)                    # :195-213 (X is NOT orthonormalised here)
+    Lam, Y = _moments_reduce(S, moments, N, m0)
+    Y, R, Lam, res = _update_R_moments(Y, Lam, T)                          # :236
+    X[:, :] = Y[:, :m0]
+    for nit in range(1, iter + 1):
+        S = contour_moments(T, X, nodes, 2 * moments, c, r, rhs=R[:, :m0], Lam=Lam[:m0])   # :255-275
+        Lam, Y = _moments_reduce(S, moments, N, m0)
+        Y, R, Lam, res = _update_R_moments(Y, Lam, T)
+        X[:, :] = Y[:, :m0]
+        inside = in_contour(Lam[:m0], c, r)
+        res_inside = res[:m0][inside]
+        if history is not None:
+            history.append((nit, int(inside.sum()), float(res_inside.max()) if inside.any() else np.nan))
+        if res_inside.size > 0 and res_inside.max() < eps:                 # :297
+            break
+        good = res_inside[res_inside < spurious]
+        if nit > 1 and good.size > 0 and good.max() < eps:                 # :300
+            break
+    normalize_cols(X)
+    return Lam, Y, res
 
 
 # --------------------------------------------------------------------------

@@ -1,5 +1,6 @@
-"""torchrun --nproc-per-node N scripts/mgpu_check.py : node-sharded gen_feast / nlfeast on N GPUs
-compared with a single-GPU run on rank 0 and with the analytic spectrum."""
+"""torchrun --nproc-per-node N scripts/mgpu_check.py : gen_feast (Krylov solves, sharded by right-hand-side columns and,
+forced, by contour nodes) and nlfeast (dense LU, node-sharded) on N GPUs compared with a single-GPU run on rank 0 and
+with the analytic spectrum."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -23,6 +24,13 @@ e, v, res = fs.gen_feast(X0.copy(), A, B, ct, eps=1e-12, iter=10, solver_opts=op
 exact = wl.laplacian3d_spectrum(m); exact = exact[np.abs(exact - c) <= r]
 ok = e.size == exact.size and np.abs(np.sort(e.real) - exact).max() < 1e-10 * exact.max() and res.max() < 1e-11
 nodes_local = st["history"][0].get("nodes_local")
+col_sharded = st["history"][0].get("col_sharded")
+ok = ok and col_sharded == 1 and nodes_local == 16            # AUTO shards the columns of a Krylov solve: all nodes on every rank
+stn = {}
+en, vn, resn = fs.gen_feast(X0.copy(), A, B, ct, eps=1e-12, iter=10, solver_opts=dict(opts, shard=_lib.SHARD_NODES), stats=stn,
+                            comm=make_comm_hook())
+ok = ok and en.size == exact.size and np.abs(np.sort(en.real) - exact).max() < 1e-10 * exact.max() and resn.max() < 1e-11
+ok = ok and stn["history"][0].get("col_sharded") == 0 and stn["history"][0].get("nodes_local") == 16 // world
 # polynomial problem, dense LU solves, two accumulators reduced
 coeffs = [a.toarray() for a in wl.butterfly_coeffs(8)]
 lam, X, rs = fs.nlfeast(coeffs, wl.rand_subspace(64, 20, seed=300), 16, 30, c=1 + 1j, r=0.5, eps=1e-12, comm=make_comm_hook())
@@ -37,7 +45,7 @@ if rank == 0:
     e1, v1, r1 = fs.gen_feast(X0.copy(), A, B, ct, eps=1e-12, iter=10, solver_opts=opts)
     ok = ok and e1.size == e.size and np.abs(np.sort(e1.real) - np.sort(e.real)).max() < 1e-11 * exact.max()
     print(json.dumps({"ok": bool(ok), "world": world, "found": int(e.size), "exact": int(exact.size),
-                      "max_res": float(res.max()), "nodes_local_rank0": nodes_local, "nl_good": int(good.sum()),
+                      "max_res": float(res.max()), "nodes_local_rank0": nodes_local, "col_sharded": col_sharded, "nl_good": int(good.sum()),
                       "allreduce_ms": st["history"][0].get("t_reduce_ms")}))
 dist.barrier()
 dist.destroy_process_group()

@@ -255,3 +255,13 @@ def test_amg_host_hierarchy_galerkin_and_convergence():
     x1_, it_amg, rel = amg_ref.pcocg(Z, b, 1e-8, 300, amg_ref.VCycle(levels, [1.0, -z]))
     assert rel < 1e-8 and it_amg * 4 < it_plain, (it_amg, it_plain)
     assert np.abs(Z @ x1_ - b).max() < 1e-6 * np.abs(b).max()
+
+
+def test_column_slices_partition_the_columns():
+    from feastsolver_jl_b200.partition import column_slice
+    for m0 in (1, 7, 20, 64, 100):
+        for nr in (1, 2, 3, 8):
+            sl = [column_slice(m0, nr, r) for r in range(nr)]
+            assert sl[0][0] == 0 and sl[-1][1] == m0
+            assert all(sl[i][1] == sl[i + 1][0] for i in range(nr - 1))
+            assert max(b - a for a, b in sl) - min(b - a for a, b in sl) <= 1

@@ -494,6 +494,52 @@ def test_nlfeast_closure_form(fs, nep_fixtures, nlfeast_golden, storage):
     assert ncalls < 16 * 6 + X0.shape[1] * 31
 
 
+@pytest.mark.parametrize("form", ["coefficients", "closure"])
+def test_one_shot_contour_solvers_and_moments(fs, nep_fixtures, form):
+    """beyn, block_SS!, nlfeast_moments! (src/beyn.jl:2-94, src/nlfeast.jl:173-318) on the device moment
+    accumulators, against the oracle restatements on identical inputs and the companion eigenvalues of the butterfly
+    problem.  block_SS! / nlfeast_moments! return a numerical-rank dependent number of extra (spurious) pairs, so the
+    comparison is on the pairs inside the contour with a small residual."""
+    coeffs = [csc_unpack(nep_fixtures, f"butterfly{i}").toarray() for i in range(5)]
+    To = fo.polynomial(coeffs)
+    T = To if form == "closure" else coeffs
+    exact = nep_fixtures["butterfly_companion_inside"]
+    rng = np.random.default_rng(3)
+    X0 = rng.random((64, 20)) + 1j * rng.random((64, 20))
+    Y = rng.random((64, 20)) + 1j * rng.random((64, 20))
+
+    def inside_good(lam, res, tol):
+        return (np.abs(lam - (1 + 1j)) <= 0.5) & (res < tol)
+    # beyn: one pass, 128 nodes, absolute residuals sorted ascending
+    lo, Xo, ro = fo.beyn(To, coeffs[0], X0.copy(), 128, c=1 + 1j, r=0.5)
+    lg, Xg, rg = fs.beyn(T, coeffs[0], X0.copy(), 128, c=1 + 1j, r=0.5)
+    assert np.all(np.diff(rg) >= 0) and Xg.shape == (64, 20)
+    go, gg = inside_good(lo, ro, 1e-9), inside_good(lg, rg, 1e-9)
+    assert gg.sum() == go.sum() == 13
+    match_eigs(lg[gg], lo[go], rtol=1e-9)
+    assert max(np.abs(exact - l).min() for l in lg[gg]) < 1e-9
+    assert rg[gg].max() <= 10 * max(ro[go].max(), 1e-13)
+    chk = np.array([np.linalg.norm(To(l) @ Xg[:, j]) for j, l in enumerate(lg)])      # absolute residual definition
+    assert np.abs(chk[gg] - rg[gg]).max() < 1e-12
+    # block_SS!
+    lo, Xo, ro = fo.block_SS(To, X0.copy(), 128, 2, c=1 + 1j, r=0.5, Y=Y)
+    lg, Xg, rg = fs.block_SS(T, X0.copy(), 128, 2, c=1 + 1j, r=0.5, Y=Y)
+    go, gg = inside_good(lo, ro, 1e-10), inside_good(lg, rg, 1e-10)
+    assert gg.sum() == go.sum() == 13 and lg.size <= 40
+    match_eigs(lg[gg], lo[go], rtol=1e-9)
+    assert rg[gg].max() <= 10 * max(ro[go].max(), 1e-13)
+    assert np.allclose(np.linalg.norm(Xg, axis=0), 1.0)
+    # nlfeast_moments!
+    Xo_, Xg_ = X0[:, :16].copy(), X0[:, :16].copy()
+    lo, Yo, ro = fo.nlfeast_moments(To, Xo_, 24, 12, c=1 + 1j, r=0.5, moments=2)
+    lg, Yg, rg = fs.nlfeast_moments(T, Xg_, 24, 12, c=1 + 1j, r=0.5, moments=2)
+    go, gg = inside_good(lo, ro, 1e-9), inside_good(lg, rg, 1e-9)
+    assert gg.sum() == go.sum() == 13
+    match_eigs(lg[gg], lo[go], rtol=1e-9)
+    assert rg[gg].max() <= 10 * max(ro[go].max(), 1e-13)
+    assert np.all(np.diff(rg) >= 0) and np.allclose(np.linalg.norm(Xg_, axis=0), 1.0)
+
+
 def test_C4_reduced_butterfly_scaled(fs):
     """C4 shape at reduced size: quartic butterfly with 24 x 24 one-dimensional blocks (n = 576, sparse
     5-point coefficient patterns through the union-pattern kernels), 24 trapezoid nodes, m0 = 24."""

@@ -20,7 +20,7 @@ def _worker(rank, world, port, out_q):
     import torch.distributed as dist
     from oracle import feast_oracle as fo
     from feastsolver_jl_b200 import workloads as wl
-    from feastsolver_jl_b200.partition import local_nodes, node_owners
+    from feastsolver_jl_b200.partition import column_slice, local_nodes, node_owners
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -38,6 +38,9 @@ def _worker(rank, world, port, out_q):
     mine = local_nodes(owners, rank)
     X0 = wl.rand_subspace(m ** 3, 16, seed=0)
     e, v, res = fo.gen_feast(X0.copy(), A, B, ct, iter=8, node_subset=mine, reduce_fn=allreduce)
+    # column sharding (the device Krylov path): every rank runs all nodes on its slice of the right-hand-side columns
+    ec, vc, resc = fo.gen_feast(X0.copy(), A, B, ct, iter=8, col_slice=column_slice(16, world, rank), reduce_fn=allreduce)
+    assert np.abs(np.sort_complex(ec) - np.sort_complex(e)).max() < 1e-11 and resc.max() < 1e-11
     # nlfeast sharded the same way (Q0 and Q1 are reduced)
     coeffs = wl.butterfly_coeffs(8)
     T = fo.polynomial([a.toarray() for a in coeffs])
