@@ -125,23 +125,44 @@ int row_grid(int nrows) {   // one warp per row, 8 warps per CTA
     return (int)(g < 1 ? 1 : (g < cap ? g : cap));
 }
 
-int cycle(feast_ctx* ctx, AmgDev* A, int l, const c128* zl, const c128* r, c128* y, c128* t) {
+// One V(1,1) cycle on level l.  The result is left in *out (y or t: the fused post-smoothing epilogue of the tiled
+// SpMM writes y_new into the other buffer because neighbouring tiles still read y as halo).  dot_rz (level 0 only,
+// optional): per-column <r, result> fused into the last kernel; *dot_done tells whether it was produced.
+int cycle(feast_ctx* ctx, AmgDev* A, int l, const c128* zl, const c128* r, c128* y, c128* t, c128** out, c128* dot_rz, bool* dot_done) {
     AmgDevLevel& L = A->lev[l];
     const int m = ctx->m0;
     cudaStream_t st = ctx->stream;
+    *out = y;
+    if (dot_done) *dot_done = false;
     if (L.nc == 0) {   // coarsest: y = Z^-1 r with the explicit inverse (row-major nc x nc)
         return launch_zgemm(ctx, L.n, m, L.n, hc128(1, 0), A->zinv, L.n, 1, false, r, m, 1, hc128(0, 0), y, m, 1);
     }
     const int64_t total = (int64_t)L.n * m;
+    AmgDevLevel& C = A->lev[l + 1];
     amg_jacobi0_kernel<<<ew_grid(total), 256, 0, st>>>(total, m, L.omega, L.dinv, r, y);
     KLAUNCH_CHECK(ctx);
-    FEAST_TRY(launch_spmm(ctx, L.n, m, L.rowptr, L.col, nullptr, zl, y, m, t, m, nullptr));
-    AmgDevLevel& C = A->lev[l + 1];
-    amg_spmm_real_kernel<false, true><<<row_grid(L.nc), 256, 0, st>>>(L.nc, m, L.r_rowptr, L.r_col, L.r_val, r, t, C.r);
+    // residual t = r - Z y, restricted: fused into the tiled SpMM's epilogue on level 0
+    int fused = l == 0 ? launch_spmm_epi(ctx, m, zl, y, t, 1, r, nullptr, 0.0, nullptr) : 1;
+    if (fused > 1) return fused;
+    if (fused == 0) {
+        amg_spmm_real_kernel<false, false><<<row_grid(L.nc), 256, 0, st>>>(L.nc, m, L.r_rowptr, L.r_col, L.r_val, t, nullptr, C.r);
+    } else {
+        FEAST_TRY(launch_spmm(ctx, L.n, m, L.rowptr, L.col, nullptr, zl, y, m, t, m, nullptr));
+        amg_spmm_real_kernel<false, true><<<row_grid(L.nc), 256, 0, st>>>(L.nc, m, L.r_rowptr, L.r_col, L.r_val, r, t, C.r);
+    }
     KLAUNCH_CHECK(ctx);
-    FEAST_TRY(cycle(ctx, A, l + 1, C.z, C.r, C.y, C.t));
-    amg_spmm_real_kernel<true, false><<<row_grid(L.n), 256, 0, st>>>(L.n, m, L.p_rowptr, L.p_col, L.p_val, C.y, nullptr, y);
+    c128* yc = nullptr;
+    FEAST_TRY(cycle(ctx, A, l + 1, C.z, C.r, C.y, C.t, &yc, nullptr, nullptr));
+    amg_spmm_real_kernel<true, false><<<row_grid(L.n), 256, 0, st>>>(L.n, m, L.p_rowptr, L.p_col, L.p_val, yc, nullptr, y);
     KLAUNCH_CHECK(ctx);
+    // post-smoothing y <- y + w D^-1 (r - Z y)
+    fused = l == 0 ? launch_spmm_epi(ctx, m, zl, y, t, 2, r, L.dinv, L.omega, dot_rz) : 1;
+    if (fused > 1) return fused;
+    if (fused == 0) {
+        *out = t;
+        if (dot_done) *dot_done = dot_rz != nullptr;
+        return 0;
+    }
     FEAST_TRY(launch_spmm(ctx, L.n, m, L.rowptr, L.col, nullptr, zl, y, m, t, m, nullptr));
     amg_jacobi_kernel<<<ew_grid(total), 256, 0, st>>>(total, m, L.omega, L.dinv, r, t, y);
     KLAUNCH_CHECK(ctx);
@@ -284,9 +305,10 @@ int amg_assemble(feast_ctx* ctx, const hc128* coef, const c128* zvals0, int* inf
     return 0;
 }
 
-// y = M^-1 r (one V-cycle on all m0 columns); t: n x m0 scratch.  r is not modified.
-int amg_apply(feast_ctx* ctx, const c128* zvals0, const c128* r, c128* y, c128* t) {
-    return cycle(ctx, ctx->amg, 0, zvals0, r, y, t);
+// M^-1 r (one V-cycle on all m0 columns) with work blocks y, t (n x m0); *out = the one holding the result.  r is not
+// modified.  dot_rz (optional): <r, M^-1 r> per column when the fused epilogue produced it (*dot_done).
+int amg_apply(feast_ctx* ctx, const c128* zvals0, const c128* r, c128* y, c128* t, c128** out, c128* dot_rz, bool* dot_done) {
+    return cycle(ctx, ctx->amg, 0, zvals0, r, y, t, out, dot_rz, dot_done);
 }
 
 int amg_info(const feast_ctx* ctx, int* nlevels, int* sizes, int cap, double* setup_seconds) {

@@ -10,7 +10,10 @@
 int launch_spmm(feast_ctx* ctx, int64_t n, int m, const int* rowptr, const int* col,
                 const double* rvals, const c128* cvals, const c128* X, int ldx, c128* Y, int ldy,
                 c128* dot_out);
-// EXPERIMENTAL mixed-precision variant: blocks stored as complex64 (n x m0, m0 even), products accumulated in double
+// fused multigrid epilogues on the union pattern (see spmm.cu); returns 1 when not applicable (caller falls back)
+int launch_spmm_epi(feast_ctx* ctx, int m, const c128* zvals, const c128* X, c128* Y, int mode, const c128* C, const c128* dinv,
+                    double omega, c128* dot_out);
+// mixed-precision variant: blocks stored as complex64 (n x m0, m0 even), products accumulated in double
 int launch_spmm_f32(feast_ctx* ctx, int m0, const c128* zvals, const void* X32, void* Y32, c128* dot_out);
 // zvals[e] = sum_i coef[i] * slotvals_i[e]   (K1 / K9: shifted / polynomial assembly)
 int launch_assemble_union(feast_ctx* ctx, int64_t unnz, int nslots, const double* const* rv,
@@ -90,7 +93,7 @@ int amg_build(feast_ctx* ctx, int64_t n, const int64_t* rowptr, const int* col, 
 void amg_free(feast_ctx* ctx);
 int amg_ensure_blocks(feast_ctx* ctx);
 int amg_assemble(feast_ctx* ctx, const hc128* coef, const c128* zvals0, int* info);
-int amg_apply(feast_ctx* ctx, const c128* zvals0, const c128* r, c128* y, c128* t);
+int amg_apply(feast_ctx* ctx, const c128* zvals0, const c128* r, c128* y, c128* t, c128** out, c128* dot_rz, bool* dot_done);
 int amg_info(const feast_ctx* ctx, int* nlevels, int* sizes, int cap, double* setup_seconds);
 
 // ---- dense.cu ------------------------------------------------------------------

@@ -7,6 +7,8 @@
 // (the reference's own inexact-solve precedent is bicgstabl, src/nlfeast.jl:106,139).
 // In residual-inverse-iteration form the solve error is relative to the shrinking ||R||,
 // which is what lets an inexact inner solve reproduce the reference's eigen-residuals.
+#include <utility>
+
 #include "kernels.cuh"
 
 namespace {
@@ -522,9 +524,17 @@ int krylov_solve_pcocg(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128*
     CUDA_TRY(ctx, cudaMemsetAsync(x, 0, bytes, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(r, Rhs, bytes, cudaMemcpyDeviceToDevice, st));
     FEAST_TRY(launch_colnorm2(ctx, n, m, r, s.bn2));
-    FEAST_TRY(amg_apply(ctx, zvals, r, z, t));
+    // z and t are the two work blocks of the cycle: the result comes back in either (fused post-smoothing epilogue)
+    auto precondition = [&](c128* dot_out) -> int {
+        c128* zr = nullptr;
+        bool dot_done = false;
+        FEAST_TRY(amg_apply(ctx, zvals, r, z, t, &zr, dot_out, &dot_done));
+        if (zr != z) std::swap(z, t);
+        if (!dot_done) FEAST_TRY(launch_coldot(ctx, n, m, r, z, false, dot_out));
+        return 0;
+    };
+    FEAST_TRY(precondition(s.rho));
     CUDA_TRY(ctx, cudaMemcpyAsync(p, z, bytes, cudaMemcpyDeviceToDevice, st));
-    FEAST_TRY(launch_coldot(ctx, n, m, r, z, false, s.rho));
     kry_init_scalars<<<1, 128, 0, st>>>(m, s, tol2);
     KLAUNCH_CHECK(ctx);
     const int rgrid = red_grid_k(n, m);
@@ -551,8 +561,7 @@ int krylov_solve_pcocg(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128*
         }
         const bool done = check && hf->nactive == 0;
         if (!done) {                                     // the last iteration needs no new direction
-            FEAST_TRY(amg_apply(ctx, zvals, r, z, t));
-            FEAST_TRY(launch_coldot(ctx, n, m, r, z, false, s.tmp1));
+            FEAST_TRY(precondition(s.tmp1));   // z = M^-1 r, tmp1 = <r, z>
             pcocg_beta_kernel<<<1, 128, 0, st>>>(m, s);
             KLAUNCH_CHECK(ctx);
         }

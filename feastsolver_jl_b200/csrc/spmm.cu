@@ -255,12 +255,17 @@ template <typename VT, typename CFG> struct TiledSmem {
 
 // G lanes own one row of the slab at a time (one accumulator per lane; up to 8 products in flight).
 // m <= 2*G: the launch covers one or two slabs.
-template <typename VT, int G, bool DOT, typename CFG>
+// EPI (fused epilogues of the multigrid cycle, amg.cu): 0 Y = S X ; 1 Y = C - S X (residual) ; 2 Y = X + w dinv (C - S X)
+// (damped-Jacobi post-smoothing step; Y must not alias X: other tiles read X rows as halo).  With DOT the fused column
+// reduction is <X, S X> for EPI 0 and <C, Y> otherwise (the <r, z> of the preconditioned COCG recurrence).
+struct SpmmEpi { int mode; const c128* C; int ldc; const c128* dinv; double omega; };
+
+template <typename VT, int G, bool DOT, typename CFG, int EPI>
 __global__ void __launch_bounds__(CFG::kThreads, CFG::kCtas)
 spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* __restrict__ t_hptr,
                   const int* __restrict__ t_hidx, const int* __restrict__ rowptr, const uint16_t* __restrict__ lcol,
                   const VT* __restrict__ val, const c128* __restrict__ X, int ldx, c128* __restrict__ Y, int ldy,
-                  double* __restrict__ partials, int dbg) {
+                  double* __restrict__ partials, int dbg, SpmmEpi ep) {
     // dbg (FEAST_SPMM_DEBUG, timing experiments only): 1 = skip the products, 2 = skip the halo copies, 4 = skip the stores
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t mbar;
@@ -339,8 +344,21 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
                     }
                 }
                 if (g < SW && !(dbg & 4)) {
-                    Y[(int64_t)(r0 + lr) * ldy + j0 + g] = acc;
-                    if (DOT) cfma(dacc[s], xs[(size_t)lr * SW + g], acc);
+                    if (EPI == 0) {
+                        Y[(int64_t)(r0 + lr) * ldy + j0 + g] = acc;
+                        if (DOT) cfma(dacc[s], xs[(size_t)lr * SW + g], acc);
+                    } else {
+                        const c128 cv = __ldg(ep.C + (int64_t)(r0 + lr) * ep.ldc + j0 + g);
+                        c128 outv = csub(cv, acc);
+                        if (EPI == 2) {
+                            const c128 wd = cscale(ep.omega, __ldg(ep.dinv + r0 + lr));
+                            const c128 resid = outv;
+                            outv = xs[(size_t)lr * SW + g];
+                            cfma(outv, wd, resid);
+                        }
+                        Y[(int64_t)(r0 + lr) * ldy + j0 + g] = outv;
+                        if (DOT) cfma(dacc[s], cv, outv);
+                    }
                 }
             }
         }
@@ -486,45 +504,49 @@ spmm_tiled_f32_kernel(int mu, int ntiles, const int* __restrict__ t_ptr, const i
     }
 }
 
-template <typename VT, int G, typename CFG>
-int spmm_tiled_launch(feast_ctx* ctx, int m, const VT* val, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
+template <typename VT, int G, typename CFG, int EPI>
+int spmm_tiled_launch(feast_ctx* ctx, int m, const VT* val, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out, SpmmEpi ep) {
     const size_t smem = TiledSmem<VT, CFG>::total(G) < 16384 ? 16384 : TiledSmem<VT, CFG>::total(G);
     static_assert(TiledSmem<VT, CFG>::total(32) <= (size_t)CFG::kBudget, "tile does not fit the CTAs-per-SM target");
     const int ntiles = ctx->ntiles;
     const int grid = ntiles < CFG::kCtas * kNumSMs ? ntiles : CFG::kCtas * kNumSMs;
-    static bool attr_done_dot[64] = {}, attr_done[64] = {};   // per device (function attributes are per context)
+    static bool attr_done_dot[64] = {}, attr_done[64] = {};   // per device and instantiation (function attributes are per context)
     const int dev = ctx->device & 63;
     static const int dbg = getenv("FEAST_SPMM_DEBUG") ? atoi(getenv("FEAST_SPMM_DEBUG")) : 0;
     if (dot_out) {
-        auto kern = spmm_tiled_kernel<VT, G, true, CFG>;
+        auto kern = spmm_tiled_kernel<VT, G, true, CFG, EPI>;
         if (!attr_done_dot[dev]) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kBudget));
             attr_done_dot[dev] = true;
         }
         kern<<<grid, CFG::kThreads, smem, ctx->stream>>>(m, ntiles, ctx->t_ptr, ctx->t_hptr, ctx->t_hidx, ctx->u_rowptr, ctx->u_lcol,
-                                                          val, X, ldx, Y, ldy, ctx->red_d, dbg);
+                                                          val, X, ldx, Y, ldy, ctx->red_d, dbg, ep);
         KLAUNCH_CHECK(ctx);
         reduce_partials_kernel<<<ceil_div(2 * m * 32, 128), 128, 0, ctx->stream>>>(ctx->red_d, grid, 2 * m, (double*)dot_out);
         KLAUNCH_CHECK(ctx);
     } else {
-        auto kern = spmm_tiled_kernel<VT, G, false, CFG>;
+        auto kern = spmm_tiled_kernel<VT, G, false, CFG, EPI>;
         if (!attr_done[dev]) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::kBudget));
             attr_done[dev] = true;
         }
         kern<<<grid, CFG::kThreads, smem, ctx->stream>>>(m, ntiles, ctx->t_ptr, ctx->t_hptr, ctx->t_hidx, ctx->u_rowptr, ctx->u_lcol,
-                                                          val, X, ldx, Y, ldy, nullptr, dbg);
+                                                          val, X, ldx, Y, ldy, nullptr, dbg, ep);
         KLAUNCH_CHECK(ctx);
     }
     return 0;
 }
 
+template <typename VT, typename CFG, int EPI>
+int spmm_tiled_dispatch_e(feast_ctx* ctx, int m, const VT* val, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out, SpmmEpi ep) {
+    if (m <= 4) return spmm_tiled_launch<VT, 4, CFG, EPI>(ctx, m, val, X, ldx, Y, ldy, dot_out, ep);
+    if (m <= 8) return spmm_tiled_launch<VT, 8, CFG, EPI>(ctx, m, val, X, ldx, Y, ldy, dot_out, ep);
+    if (m <= 16) return spmm_tiled_launch<VT, 16, CFG, EPI>(ctx, m, val, X, ldx, Y, ldy, dot_out, ep);
+    return spmm_tiled_launch<VT, 32, CFG, EPI>(ctx, m, val, X, ldx, Y, ldy, dot_out, ep);   // m <= 64: one or two slabs of 32 columns
+}
 template <typename VT, typename CFG>
 int spmm_tiled_dispatch_g(feast_ctx* ctx, int m, const VT* val, const c128* X, int ldx, c128* Y, int ldy, c128* dot_out) {
-    if (m <= 4) return spmm_tiled_launch<VT, 4, CFG>(ctx, m, val, X, ldx, Y, ldy, dot_out);
-    if (m <= 8) return spmm_tiled_launch<VT, 8, CFG>(ctx, m, val, X, ldx, Y, ldy, dot_out);
-    if (m <= 16) return spmm_tiled_launch<VT, 16, CFG>(ctx, m, val, X, ldx, Y, ldy, dot_out);
-    return spmm_tiled_launch<VT, 32, CFG>(ctx, m, val, X, ldx, Y, ldy, dot_out);   // m <= 64: one or two slabs of 32 columns
+    return spmm_tiled_dispatch_e<VT, CFG, 0>(ctx, m, val, X, ldx, Y, ldy, dot_out, SpmmEpi{0, nullptr, 0, nullptr, 0.0});
 }
 
 int tile_cfg_setting() {
@@ -577,6 +599,24 @@ int launch_spmm(feast_ctx* ctx, int64_t n, int m, const int* rowptr, const int* 
         else
             rc = rvals ? spmm_dispatch<double>(ctx, (int)n, mc, rowptr, col, rvals, X + j0, ldx, Y + j0, ldy, dchunk)
                        : spmm_dispatch<c128>(ctx, (int)n, mc, rowptr, col, cvals, X + j0, ldx, Y + j0, ldy, dchunk);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// Tiled SpMM with a fused multigrid epilogue on the union pattern (complex values, default tile configuration):
+//   mode 1: Y = C - Z X ; mode 2: Y = X + omega dinv (C - Z X).  dot_out (optional): <C, Y> per column (unconjugated).
+// Returns 1 when the fused kernel is not applicable (no tile plan / other tile configuration): the caller falls back.
+int launch_spmm_epi(feast_ctx* ctx, int m, const c128* zvals, const c128* X, c128* Y, int mode, const c128* C, const c128* dinv,
+                    double omega, c128* dot_out) {
+    static const bool off = getenv("FEAST_SPMM_EPI") && atoi(getenv("FEAST_SPMM_EPI")) == 0;
+    if (off || !ctx->tiles_ok || ctx->tile_cfg != 0) return 1;
+    for (int j0 = 0; j0 < m; j0 += 64) {
+        const int mc = (m - j0) < 64 ? (m - j0) : 64;
+        SpmmEpi ep{mode, C + j0, m, dinv, omega};
+        c128* dchunk = dot_out ? dot_out + j0 : nullptr;
+        int rc = mode == 1 ? spmm_tiled_dispatch_e<c128, TileCfg0, 1>(ctx, mc, zvals, X + j0, m, Y + j0, m, dchunk, ep)
+                           : spmm_tiled_dispatch_e<c128, TileCfg0, 2>(ctx, mc, zvals, X + j0, m, Y + j0, m, dchunk, ep);
         if (rc) return rc;
     }
     return 0;

@@ -176,7 +176,7 @@ int launch_zgemm(feast_ctx* ctx, int M, int N, int64_t K, hc128 alpha, const c12
     }
     int splitk = 1;
     const bool beta_zero = (beta == hc128(0.0, 0.0));
-    if (beta_zero && (int64_t)gx * gy < kNumSMs && K >= 4096) {  // tall-skinny (Gram): split K over the SMs
+    if (beta_zero && (int64_t)gx * gy < kNumSMs && K >= 1024) {  // tall-skinny (Gram) / skinny right-hand sides: split K over the SMs
         splitk = (2 * kNumSMs) / (gx * gy);
         int64_t maxsplit = K / 512;
         if (splitk > maxsplit) splitk = (int)maxsplit;
