@@ -13,7 +13,7 @@ module FEASTSolverB200
 using LinearAlgebra
 using SparseArrays
 
-export feast!, gen_feast!, dual_gen_feast!, nlfeast!, ifeast!, contour_estimate_eig
+export feast!, gen_feast!, dual_gen_feast!, nlfeast!, ifeast!, contour_estimate_eig, beyn, block_SS!, nlfeast_moments!
 export in_contour, circular_contour_trapezoidal, circular_contour_gauss,
        rectangular_contour_gauss, rectangular_contour_trapezoidal, rational_func
 export Contour, CircularContour, RectangularContour, CustomContour
@@ -372,6 +372,150 @@ function nlfeast!(T::Function, X::AbstractMatrix{ComplexF64}, nodes::Integer, it
     _ck(ctx, ccall((:feast_get_X, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Int64), ctx.h, X, N))
     finalize(ctx)
     Λ, X, res
+end
+
+# ---------------------------------------------------------------- one-shot contour solvers and higher moments
+# beyn / block_SS! / nlfeast_moments! (src/beyn.jl:2-94, src/nlfeast.jl:173-318) over the device moment accumulators
+# S_p = sum_k w_k z_k^p (...)  (feast_set_moments: a p-loop in the accumulate kernel).  `T` is the coefficient list
+# (device assembly); the closure form goes through the sampled-operator entries exactly as in nlfeast!(T::Function, ...).
+function _nep_ctx(T::AbstractVector{<:AbstractMatrix}, X, nodes, c, r, store)
+    N, m₀ = size(X)
+    ctx = FeastCtx()
+    for (i, Ai) in enumerate(T)
+        _set_operator!(ctx, i - 1, Ai, N)
+    end
+    _ck(ctx, ccall((:feast_set_problem, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint), ctx.h, 2, length(T)))
+    contour = circular_contour_trapezoidal(c, r, nodes)
+    z = convert(Vector{ComplexF64}, contour.nodes); w = convert(Vector{ComplexF64}, contour.weights)
+    _ck(ctx, ccall((:feast_set_contour, libfeast), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}), ctx.h, nodes, z, w))
+    _ck(ctx, ccall((:feast_set_solver, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cint, Cint), ctx.h, 0, 0, 1e-8, 4000, store))
+    Xc = convert(Matrix{ComplexF64}, X)
+    _ck(ctx, ccall((:feast_set_subspace, libfeast), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{ComplexF64}, Int64), ctx.h, N, m₀, Xc, N))
+    ctx
+end
+_moments!(ctx, k) = _ck(ctx, ccall((:feast_set_moments, libfeast), Cint, (Ptr{Cvoid}, Cint), ctx.h, k))
+_pass!(ctx, Λ, first) = _ck(ctx, ccall((:feast_contour_apply, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Cint, Ptr{Cvoid}),
+                                       ctx.h, Λ, first, C_NULL); allow=(0, 2000))
+function _gram(ctx, a, b, m₀)
+    G = zeros(ComplexF64, m₀, m₀)
+    _ck(ctx, ccall((:feast_block_gram, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{ComplexF64}), ctx.h, a, b, G))
+    G
+end
+function _combine_residual!(ctx, W, λ, N, m₀)          # X = [S_0 .. S_{k-1}] W ; normalise ; relative residuals
+    _ck(ctx, ccall((:feast_moment_combine, libfeast), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Int64), ctx.h, size(W, 1) ÷ m₀, W, size(W, 1)))
+    res = Array{Float64}(undef, m₀)
+    _ck(ctx, ccall((:feast_recover_residual, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Cdouble}), ctx.h, C_NULL, λ, res))
+    res
+end
+function _getX(ctx, N, m₀)
+    X = Matrix{ComplexF64}(undef, N, m₀)
+    _ck(ctx, ccall((:feast_get_X, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Int64), ctx.h, X, N))
+    X
+end
+
+function beyn(T::AbstractVector{<:AbstractMatrix}, A::AbstractMatrix, X::AbstractMatrix, nodes::Integer; c=complex(0.0, 0.0), r=1.0)
+    N, m₀ = size(X)
+    size(A, 1) != size(A, 2) && error("Incorrect dimensions of A, must be square")
+    size(A, 1) != N && error("Incorrect dimensions of X₀, must match A")
+    ctx = _nep_ctx(T, X, nodes, c, r, false)
+    _moments!(ctx, 2)
+    _pass!(ctx, zeros(ComplexF64, m₀), 1)                                               # beyn.jl:16-21
+    Rf, G1 = zeros(ComplexF64, m₀, m₀), zeros(ComplexF64, m₀, m₀)
+    _ck(ctx, ccall((:feast_beyn_reduce, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}), ctx.h, Rf, G1))
+    S = svd!(copy(Rf)); F = eigen!((S.U' * G1) * S.V * Diagonal(1 ./ S.S))              # beyn.jl:22-24
+    Λ = convert(Vector{ComplexF64}, F.values); Xq = convert(Matrix{ComplexF64}, S.U * F.vectors)
+    res = Array{Float64}(undef, m₀); fro = Array{Float64}(undef, m₀)
+    _ck(ctx, ccall((:feast_recover_residual, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Cdouble}), ctx.h, Xq, Λ, res))
+    _ck(ctx, ccall((:feast_last_fro, libfeast), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), ctx.h, fro))
+    Xn = _getX(ctx, N, m₀); finalize(ctx)
+    res .*= fro                                                                         # absolute residual, beyn.jl:28
+    p = sortperm(res)
+    Λ[p], Xn[:, p], res[p]
+end
+
+function block_SS!(T::AbstractVector{<:AbstractMatrix}, X::AbstractMatrix{ComplexF64}, nodes=2^4, moments=2;
+                   c=complex(0.0, 0.0), r=1.0, debug=false, Y=rand(ComplexF64, size(X)...))
+    N, m₀ = size(X); K = moments * m₀
+    ctx = _nep_ctx(T, X, nodes, c, r, false)
+    _ck(ctx, ccall((:feast_orthonormalize_X, libfeast), Cint, (Ptr{Cvoid},), ctx.h))    # beyn.jl:41
+    _moments!(ctx, 2 * moments + 1)
+    _pass!(ctx, zeros(ComplexF64, m₀), 1)                                               # beyn.jl:50-56
+    _ck(ctx, ccall((:feast_set_X, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Int64), ctx.h, convert(Matrix{ComplexF64}, Y), N))
+    G = [_gram(ctx, -1, p, m₀) for p = 0:2*moments]                                     # Y' * S_p
+    Q₀, Q₁ = zeros(ComplexF64, m₀ * moments, K), zeros(ComplexF64, m₀ * moments, K)
+    for i = 1:moments, j = 1:moments
+        Q₀[(i-1)*m₀+1:i*m₀, (j-1)*m₀+1:j*m₀] .= G[i+j]                                  # S_{i+j-1}, beyn.jl:66
+        Q₁[(i-1)*m₀+1:i*m₀, (j-1)*m₀+1:j*m₀] .= G[i+j+1]                                # S_{i+j},   beyn.jl:67
+    end
+    V = svd(Q₀); n = min(count(V.S / V.S[1] .> 1e-13), K)                               # beyn.jl:77-78
+    Λ, Xq = eigen!(V.U[:, 1:n]' * Q₁ * V.V[:, 1:n], V.U[:, 1:n]' * Q₀ * V.V[:, 1:n])     # beyn.jl:80-83
+    W = V.V[:, 1:n] * Xq
+    Xn = Matrix{ComplexF64}(undef, N, n); res = zeros(n)
+    for c0 = 1:m₀:n                                                                     # the device block is m0 wide
+        c1 = min(n, c0 + m₀ - 1); k = c1 - c0 + 1
+        Wc = repeat(W[:, c0:c0], 1, m₀); Wc[:, 1:k] .= W[:, c0:c1]
+        λc = fill(ComplexF64(Λ[c0]), m₀); λc[1:k] .= Λ[c0:c1]
+        rc = _combine_residual!(ctx, convert(Matrix{ComplexF64}, Wc), λc, N, m₀)        # beyn.jl:87-93
+        Xn[:, c0:c1] .= _getX(ctx, N, m₀)[:, 1:k]; res[c0:c1] .= rc[1:k]
+    end
+    finalize(ctx)
+    Λ, Xn, res
+end
+
+# nlfeast_moments!: the tall SVD of the block-Hankel matrix is formed from m0 x m0 Gram blocks S_a' S_b (see DESIGN.md);
+# directions below 1e-7 of the largest singular value are dropped.
+function nlfeast_moments!(T::AbstractVector{<:AbstractMatrix}, X::AbstractMatrix{ComplexF64}, nodes::Integer, iter::Integer;
+                          c=complex(0.0, 0.0), r=1.0, debug=false, ϵ=10e-12, moments=2, store=true, spurious=1e-5)
+    N, m₀ = size(X); M = moments; K = M * m₀
+    ctx = _nep_ctx(T, X, nodes, c, r, store)
+    _moments!(ctx, 2M)
+    Λ = ComplexF64[]; res = Float64[]; W = zeros(ComplexF64, K, 0); λx = zeros(ComplexF64, m₀)
+    function reduce!()
+        g(a, b) = a <= b ? _gram(ctx, a, b, m₀) : Matrix(_gram(ctx, b, a, m₀)')
+        G0, G01 = zeros(ComplexF64, K, K), zeros(ComplexF64, K, K)
+        for j = 0:M-1, jp = 0:M-1
+            G0[j*m₀+1:(j+1)*m₀, jp*m₀+1:(jp+1)*m₀] .= sum(g(i + j, i + jp) for i = 0:M-1)
+            G01[j*m₀+1:(j+1)*m₀, jp*m₀+1:(jp+1)*m₀] .= sum(g(i + j, i + jp + 1) for i = 0:M-1)
+        end
+        E = eigen(Hermitian((G0 + G0') / 2)); ev = reverse(E.values); Vv = E.vectors[:, end:-1:1]
+        keep = ev .> 1e-14 * ev[1]; sv = sqrt.(ev[keep]); Vv = Vv[:, keep]
+        F = eigen!(Diagonal(1 ./ sv) * (Vv' * G01 * Vv) * Diagonal(1 ./ sv))             # nlfeast.jl:222-225
+        Wn = Vv * Diagonal(1 ./ sv) * F.vectors; λ = convert(Vector{ComplexF64}, F.values); nk = length(λ)
+        rs = zeros(nk)
+        for c0 = 1:m₀:nk
+            c1 = min(nk, c0 + m₀ - 1); k = c1 - c0 + 1
+            Wc = repeat(Wn[:, c0:c0], 1, m₀); Wc[:, 1:k] .= Wn[:, c0:c1]
+            λc = fill(λ[c0], m₀); λc[1:k] .= λ[c0:c1]
+            rs[c0:c1] .= _combine_residual!(ctx, convert(Matrix{ComplexF64}, Wc), λc, N, m₀)[1:k]
+        end
+        p = sortperm(rs); Λ = λ[p]; res = rs[p]; W = Wn[:, p]                            # utils.jl:125-133
+        nb = min(m₀, nk); Wc = repeat(W[:, 1:1], 1, m₀); Wc[:, 1:nb] .= W[:, 1:nb]
+        λx = fill(Λ[1], m₀); λx[1:nb] .= Λ[1:nb]
+        _combine_residual!(ctx, convert(Matrix{ComplexF64}, Wc), λx, N, m₀)             # X = Y[:, 1:m0] and its R
+    end
+    _pass!(ctx, zeros(ComplexF64, m₀), 1); reduce!()                                    # nlfeast.jl:195-236
+    for nit = 1:iter
+        _pass!(ctx, λx, 0); reduce!()                                                   # nlfeast.jl:255-283
+        nb = min(m₀, length(Λ))
+        res_inside = res[1:nb][in_contour.(Λ[1:nb], c, r)]
+        if size(res_inside, 1) > 0 && maximum(res_inside) < ϵ
+            break
+        end
+        if nit > 1 && sum(res_inside .< spurious) > 0 && maximum(res_inside[res_inside .< spurious]) < ϵ
+            break
+        end
+    end
+    X .= _getX(ctx, N, m₀)
+    Yall = Matrix{ComplexF64}(undef, N, length(Λ))
+    for c0 = 1:m₀:length(Λ)
+        c1 = min(length(Λ), c0 + m₀ - 1); k = c1 - c0 + 1
+        Wc = repeat(W[:, c0:c0], 1, m₀); Wc[:, 1:k] .= W[:, c0:c1]
+        λc = fill(Λ[c0], m₀); λc[1:k] .= Λ[c0:c1]
+        _combine_residual!(ctx, convert(Matrix{ComplexF64}, Wc), λc, N, m₀)
+        Yall[:, c0:c1] .= _getX(ctx, N, m₀)[:, 1:k]
+    end
+    finalize(ctx)
+    Λ, Yall, res
 end
 
 # ---------------------------------------------------------------- fine-grained plugin path
