@@ -19,6 +19,9 @@ def make_comm_hook(contour_nodes=None, balanced=True):
     world, rank = dist.get_world_size(), dist.get_rank()
 
     def hook(ctx):
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.set_device(ctx.device)   # the hook may run on a helper thread: the current device is per thread
         lib = _lib.load()
         payload = [None]
         if rank == 0:

@@ -437,6 +437,17 @@ def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, 
     tick("ctx_create_s")
     try:
         A, B = _densify_if_mixed(A, B)
+        comm_thread, comm_err = None, []
+        if comm is not None:   # NCCL bootstrap (id broadcast + ncclCommInitRank, ~1 s) overlaps the host-side layout build
+            import threading
+
+            def _comm():
+                try:
+                    comm(ctx)
+                except BaseException as e:   # re-raised on the calling thread below
+                    comm_err.append(e)
+            comm_thread = threading.Thread(target=_comm)
+            comm_thread.start()
         ctx.set_solver(store=store, **solver_opts)   # before the operators: the device layout is then built once
         ctx.set_operator(0, A)
         if generalized:
@@ -444,9 +455,11 @@ def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, 
         tick("upload_operators_s")                   # host CSC -> CSR (+ symmetry check), dense uploads
         ctx.set_problem(_lib.PROBLEM_GENERALIZED if generalized else _lib.PROBLEM_STANDARD, 2 if generalized else 1, N)
         tick("build_layout_s")                       # union pattern, tile plan, multigrid hierarchy, uploads
-        if comm is not None:
-            comm(ctx)
-        tick("comm_init_s")
+        if comm_thread is not None:
+            comm_thread.join()
+            if comm_err:
+                raise comm_err[0]
+        tick("comm_init_wait_s")
         ctx.set_contour(contour.nodes, contour.weights)
         if ctx.nranks > 1:  # balanced node -> rank map (near-axis nodes cost more Krylov iterations)
             ctx.set_node_owners(node_owners(contour.nodes, ctx.nranks))
