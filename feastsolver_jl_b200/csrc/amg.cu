@@ -91,7 +91,26 @@ amg_spmm_real_kernel(int nrows, int m, const int* __restrict__ rowptr, const int
         for (int j0 = 0; j0 < m; j0 += 64) {
             const int ja = j0 + lane, jb = j0 + 32 + lane;
             c128 a0 = cmake(0.0, 0.0), a1 = cmake(0.0, 0.0);
-            for (int e = e0; e < e1; ++e) {
+            int e = e0;
+            for (; e + 4 <= e1; e += 4) {   // four entries in flight: the gathers are L2 latency bound
+                int64_t c[4];
+                double v[4];
+                c128 xa[4], xb[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { c[q] = __ldg(col + e + q); v[q] = __ldg(val + e + q); }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    xa[q] = ja < m ? __ldg(X1 + c[q] * m + ja) : cmake(0.0, 0.0);
+                    xb[q] = jb < m ? __ldg(X1 + c[q] * m + jb) : cmake(0.0, 0.0);
+                    if (DIFF) {
+                        if (ja < m) xa[q] = csub(xa[q], __ldg(X2 + c[q] * m + ja));
+                        if (jb < m) xb[q] = csub(xb[q], __ldg(X2 + c[q] * m + jb));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { rfma(a0, v[q], xa[q]); rfma(a1, v[q], xb[q]); }
+            }
+            for (; e < e1; ++e) {
                 const int64_t c = __ldg(col + e);
                 const double v = __ldg(val + e);
                 if (ja < m) {
