@@ -104,7 +104,8 @@ def build_workload(grid):
     from feastsolver_jl_b200 import workloads as wl
     A, B = wl.laplacian3d_pencil(grid)
     c, r, cnt = wl.c2_slice(grid, target=TARGET)
-    X0 = wl.rand_subspace(grid ** 3, M0, seed=0)
+    # column-major like Julia's Matrix{ComplexF64} (the layout that crosses the ABI): no host-side transposes in the timed region
+    X0 = np.asfortranarray(wl.rand_subspace(grid ** 3, M0, seed=0))
     return A, B, c, r, cnt, X0
 
 
@@ -194,7 +195,7 @@ def e2e_solve(fs, A, B, contour, X0, solver_opts, device, hook):
     """The public call with HOST buffers, run to convergence (context creation, operator upload, layout build, all
     outer iterations and the download of X inside the timed region)."""
     st = {}
-    Xh = X0.copy()
+    Xh = X0.copy(order="F")
     t0 = time.perf_counter()
     ctx = fs.FeastContext(device=device)
     e, v, rs = fs.gen_feast(Xh, A, B, contour, eps=EPS, iter=10, ctx=ctx, solver_opts=solver_opts, stats=st, comm=hook)

@@ -21,6 +21,9 @@ int host_threads() {
         int v = e ? atoi(e) : 0;
         if (v <= 0) {
             v = (int)std::thread::hardware_concurrency();
+            const char* lw = getenv("LOCAL_WORLD_SIZE");      // one process per GPU: share the host cores between the ranks
+            const int ranks = lw ? atoi(lw) : 1;
+            if (ranks > 1) v = v / ranks;
             if (v > 16) v = 16;
         }
         return v < 1 ? 1 : v;
