@@ -299,9 +299,9 @@ def run_ours(args):
     launches = int(sum_over_ranks(ctx.launch_count() - launches0))
     spmm_ms = max_over_ranks(agg["t_spmm_ms"] / max(1, agg["spmm_launches"]))
     inner_total = int(sum_over_ranks(agg["inner_iters_total"]))
-    col_sharded = bool(st.get("col_sharded", 0))
+    col_sharded = int(st.get("col_sharded", 0))
     if col_sharded:
-        inner_total //= world     # every rank ran every node on its own slice of the right-hand-side columns
+        inner_total //= col_sharded     # every node ran on `col_sharded` ranks, each on its own slice of the right-hand-side columns
     reduce_ms = max_over_ranks(agg["t_reduce_ms"])
     solve_ms_max, solve_ms_sum = max_over_ranks(agg["t_solve_ms"] + agg["t_factor_ms"]), sum_over_ranks(agg["t_solve_ms"] + agg["t_factor_ms"])
     value = NODES * args.steps / (ms / 1e3)
@@ -360,8 +360,8 @@ def run_ours(args):
                    "timed_steps": "real pre-convergence passes only (solve restarted from X0 when it converges inside the "
                                   f"timed region; {restarts} restart(s))",
                    "l2_policy": "inputs (5 GB of Krylov blocks) exceed the 126 MB L2",
-                   "sharding": ("columns: every rank solves all nodes on m0/N right-hand-side columns" if col_sharded
-                                else "contour nodes") if world > 1 else "single GPU",
+                   "sharding": (f"{world // col_sharded} node group(s) x {col_sharded} column slice(s) of the right-hand sides "
+                                "(groups chosen from the measured node costs)" if col_sharded else "contour nodes") if world > 1 else "single GPU",
                    "node_owners": [int(o) for o in owners],
                    "layout": {"rows_renumbered": layout["reordered"], "spmm_tiles": layout["ntiles"],
                               "halo_rows_per_row": round(layout["halo_rows_per_row"], 3)}},

@@ -28,6 +28,13 @@ struct AmgDev {
     int ncoarse = 0;
     c128 *zd = nullptr, *zinv = nullptr, *ident = nullptr, *cwork = nullptr, *dinvb = nullptr;
     int *ipiv = nullptr, *perm = nullptr;
+    // The contour nodes do not change between outer iterations, so the explicit inverse of a node's coarsest operator
+    // (LU + nc right-hand sides: the dominant per-node setup cost, ~50 ms at nc = 2788) is kept per node and reused by every
+    // later pass.  key = the node's coefficients; dropped with the contour (feast_set_contour) or the problem.
+    struct CachedInverse { c128* zinv = nullptr; hc128 coef[FEAST_MAX_SLOTS]; };
+    std::vector<CachedInverse> cache;
+    c128* zinv_scratch = nullptr;    // inverse of an uncached solve (node index < 0 or cache budget exhausted)
+    int64_t cache_bytes = 0;
     double setup_seconds = 0.0;
     int64_t bytes = 0;
 };
@@ -200,7 +207,8 @@ void amg_free(feast_ctx* ctx) {
         fr(L.p_rowptr); fr(L.p_col); fr(L.p_val); fr(L.r_rowptr); fr(L.r_col); fr(L.r_val);
         fr(L.r); fr(L.y); fr(L.t);
     }
-    fr(A->zd); fr(A->zinv); fr(A->ident); fr(A->cwork); fr(A->dinvb); fr(A->ipiv); fr(A->perm);
+    fr(A->zd); fr(A->zinv_scratch); fr(A->ident); fr(A->cwork); fr(A->dinvb); fr(A->ipiv); fr(A->perm);
+    for (auto& c : A->cache) fr(c.zinv);
     delete A;
     ctx->amg = nullptr;
 }
@@ -262,7 +270,8 @@ int amg_build(feast_ctx* ctx, int64_t n, const int64_t* rowptr, const int* col, 
     const int nc = A->lev.back().n;
     A->ncoarse = nc;
     FEAST_TRY(alloc(ctx, &A->zd, (size_t)nc * nc, A));
-    FEAST_TRY(alloc(ctx, &A->zinv, (size_t)nc * nc, A));
+    FEAST_TRY(alloc(ctx, &A->zinv_scratch, (size_t)nc * nc, A));
+    A->zinv = A->zinv_scratch;
     FEAST_TRY(alloc(ctx, &A->ident, (size_t)nc * nc, A));
     FEAST_TRY(alloc(ctx, &A->cwork, (size_t)nc * nc, A));
     FEAST_TRY(alloc(ctx, &A->dinvb, (size_t)2 * nc * kDiagNB, A));
@@ -292,9 +301,10 @@ int amg_ensure_blocks(feast_ctx* ctx) {
 // Shifted operators of every level for one contour node: z_l = sum_i coef[i] slot_i, Jacobi diagonals, and the
 // explicit inverse of the coarsest one (dense LU + solve against the identity).  Level 0 uses ctx->zvals (assembled
 // by the caller).
-int amg_assemble(feast_ctx* ctx, const hc128* coef, const c128* zvals0, int* info) {
+int amg_assemble(feast_ctx* ctx, const hc128* coef, const c128* zvals0, int node, int* info) {
     AmgDev* A = ctx->amg;
     cudaStream_t st = ctx->stream;
+    if (info) *info = 0;
     for (size_t l = 0; l < A->lev.size(); ++l) {
         AmgDevLevel& L = A->lev[l];
         const c128* z = zvals0;
@@ -314,14 +324,42 @@ int amg_assemble(feast_ctx* ctx, const hc128* coef, const c128* zvals0, int* inf
     }
     AmgDevLevel& C = A->lev.back();
     const int nc = C.n;
+    // cached inverse of this node?
+    static const int64_t budget = (getenv("FEAST_AMG_CACHE_GB") ? atoll(getenv("FEAST_AMG_CACHE_GB")) : 16) << 30;
+    AmgDev::CachedInverse* slot = nullptr;
+    if (node >= 0) {
+        if ((int)A->cache.size() <= node) A->cache.resize(node + 1);
+        slot = &A->cache[node];
+        bool same = slot->zinv != nullptr;
+        for (int s = 0; s < A->nslots && same; ++s) same = slot->coef[s] == coef[s];
+        if (same) { A->zinv = slot->zinv; return 0; }
+        if (!slot->zinv) {
+            const int64_t bytes = (int64_t)sizeof(c128) * nc * nc;
+            if (A->cache_bytes + bytes <= budget && cudaMalloc((void**)&slot->zinv, bytes) == cudaSuccess) A->cache_bytes += bytes;
+            else { cudaGetLastError(); slot->zinv = nullptr; slot = nullptr; }
+        }
+    }
+    c128* dst = slot ? slot->zinv : A->zinv_scratch;
     FEAST_TRY(launch_scatter_dense(ctx, nc, C.rowptr, C.col, C.z, A->zd));
     int inf = 0;
     FEAST_TRY(dense_getrf(ctx, nc, A->zd, A->ipiv, &inf));
     if (info) *info = inf;
     FEAST_TRY(dense_build_perm(ctx, nc, A->ipiv, A->perm));
     FEAST_TRY(dense_build_diag_inverses(ctx, nc, A->zd, A->dinvb));
-    FEAST_TRY(dense_getrs(ctx, nc, A->zd, A->perm, A->dinvb, nc, A->ident, A->zinv, false, A->cwork));
+    FEAST_TRY(dense_getrs(ctx, nc, A->zd, A->perm, A->dinvb, nc, A->ident, dst, false, A->cwork));
+    if (slot) for (int s = 0; s < FEAST_MAX_SLOTS; ++s) slot->coef[s] = s < A->nslots ? coef[s] : hc128(0, 0);
+    A->zinv = dst;
     return 0;
+}
+
+// the contour changed: the cached coarse inverses belong to the old nodes
+void amg_drop_cache(feast_ctx* ctx) {
+    AmgDev* A = ctx->amg;
+    if (!A) return;
+    for (auto& c : A->cache) fr(c.zinv);
+    A->cache.clear();
+    A->cache_bytes = 0;
+    A->zinv = A->zinv_scratch;
 }
 
 // M^-1 r (one V-cycle on all m0 columns) with work blocks y, t (n x m0); *out = the one holding the result.  r is not

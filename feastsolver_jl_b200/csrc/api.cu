@@ -590,6 +590,42 @@ void rebalance_nodes(feast_ctx* ctx) {
     }
 }
 
+// Column sharding in GROUPS (Krylov inner solves, several ranks): the ranks are split into G groups of nranks / G; a node
+// belongs to one group, whose ranks each solve m0 / (nranks / G) of its right-hand-side columns.  G = 1 is the pure
+// column split (balanced by construction, used in the first pass when no costs are known); larger G means wider, more
+// efficient column slices (the per-iteration time has a fixed part: coarse multigrid levels, launch latencies --
+// measured 7.15 ms at 64 columns, 4.75 ms at 32) but needs the node costs to balance the groups.  From the costs
+// measured in the previous pass every divisor G of nranks is scored by
+//     (LPT makespan over G groups) x (columns per rank + fixed), fixed = 12 columns (FEAST_SHARD_FIXED_COLS)
+// and the best one is taken; identical on every rank (the cost vector is all-reduced).
+void choose_groups(feast_ctx* ctx) {
+    static const double fixed_cols = getenv("FEAST_SHARD_FIXED_COLS") ? atof(getenv("FEAST_SHARD_FIXED_COLS")) : 12.0;
+    static const int forced = getenv("FEAST_SHARD_GROUPS") ? atoi(getenv("FEAST_SHARD_GROUPS")) : 0;
+    const int nn = (int)ctx->znodes.size(), nr = ctx->nranks;
+    ctx->ngroups = 1;
+    ctx->gowner.assign(nn, 0);
+    if (!ctx->have_costs && !forced) return;
+    std::vector<int> order(nn);
+    for (int k = 0; k < nn; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ctx->node_cost[a] > ctx->node_cost[b]; });
+    double best = -1.0;
+    for (int G = 1; G <= nr; ++G) {
+        if (nr % G != 0 || (forced && G != forced)) continue;
+        const int gs = nr / G;
+        if (ctx->m0 < 2 * gs && gs > 1) continue;
+        std::vector<double> load(G, 0.0);
+        std::vector<int> own(nn, 0);
+        for (int k : order) {
+            int b = 0;
+            for (int g = 1; g < G; ++g) if (load[g] < load[b]) b = g;
+            own[k] = b;
+            load[b] += ctx->have_costs ? ctx->node_cost[k] : 1.0;
+        }
+        const double score = *std::max_element(load.begin(), load.end()) * ((double)ctx->m0 / gs + fixed_cols);
+        if (best < 0.0 || score < best) { best = score; ctx->ngroups = G; ctx->gowner = own; }
+    }
+}
+
 // W = op(slot)^H * V.  Dense: one DMMA GEMM on the conjugate-transposed view.  Sparse: supported when
 // the slot is (complex-)symmetric, op^H = conj(op): W = conj(op * conj(V)).
 int apply_slot_adjoint(feast_ctx* ctx, int slot, const c128* V, c128* W) {
@@ -616,10 +652,10 @@ int apply_slot_adjoint(feast_ctx* ctx, int slot, const c128* V, c128* W) {
 
 // Krylov inner solve; COCG with complex64 block storage when mixed precision was requested and is applicable
 int krylov_any(feast_ctx* ctx, int method, const hc128* coef, const c128* zvals, const c128* rhs, c128* Y, KrylovResult* kr,
-               feast_stats* st) {
+               feast_stats* st, int node = -1) {
     if (ctx->amg && method == FEAST_KRYLOV_COCG && !ctx->mixed_prec) {
         int info = 0;
-        FEAST_TRY(amg_assemble(ctx, coef, zvals, &info));
+        FEAST_TRY(amg_assemble(ctx, coef, zvals, node, &info));
         if (info) return feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d of the coarsest multigrid operator", info);
         if (st) amg_info(ctx, &st->precond_levels, nullptr, 0, nullptr);
         return krylov_solve_pcocg(ctx, zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, kr);
@@ -697,7 +733,7 @@ int solve_shifted(feast_ctx* ctx, int solver, int method, int k, const hc128* co
             FEAST_TRY(krylov_any(ctx, method, coef, ctx->zvals, ctx->W2.p, Y, &kr, &st));   // same Z, conjugated data
             FEAST_TRY(launch_conj(ctx, n * m, Y, Y));
         } else {
-            FEAST_TRY(krylov_any(ctx, method, coef, ctx->zvals, rhs, Y, &kr, &st));
+            FEAST_TRY(krylov_any(ctx, method, coef, ctx->zvals, rhs, Y, &kr, &st, k));
         }
         st.inner_iters_total += kr.iters;
         st.inner_iters_max = std::max(st.inner_iters_max, kr.iters);
@@ -933,6 +969,7 @@ int feast_set_contour(feast_ctx* ctx, int nnodes, const feast_c128* z, const fea
     ctx->node_cost.assign(nnodes, 0.0);
     ctx->have_costs = false;
     drop_stored_factors(ctx);   // the factors belong to the old nodes
+    amg_drop_cache(ctx);
     return 0;
 }
 
@@ -1321,8 +1358,16 @@ static int contour_begin(feast_ctx* ctx, int solver) {
     for (int p = 0; p < contour_nmom(ctx); ++p)                                                // feast.jl:58, nlfeast.jl:32-33
         CUDA_TRY(ctx, cudaMemsetAsync(moment_block(ctx, p), 0, sizeof(c128) * n * m, ctx->stream));
     if (contour_can_move_nodes(ctx, solver) && ctx->have_costs) rebalance_nodes(ctx);
+    if (ctx->col_shard) choose_groups(ctx);
     ctx->cost_local.assign(ctx->znodes.size(), 0.0);
     return 0;
+}
+
+// does this rank take part in node k of the running pass?
+static bool contour_my_node(const feast_ctx* ctx, int k) {
+    if (!ctx->col_shard) return ctx->owner[k] == ctx->rank;
+    const int gs = ctx->nranks / ctx->ngroups;
+    return ctx->gowner[k] == ctx->rank / gs;
 }
 
 static int contour_node(feast_ctx* ctx, int k, const feast_c128* lambda, int first_pass, int solver, int method, feast_stats& st,
@@ -1337,7 +1382,7 @@ static int contour_node(feast_ctx* ctx, int k, const feast_c128* lambda, int fir
     (void)nep;
     const c128* rhs = first_pass ? ctx->X.p : ctx->R.p;
     st.nodes_local++;
-    st.col_sharded = ctx->col_shard ? 1 : 0;
+    st.col_sharded = ctx->col_shard ? ctx->nranks / ctx->ngroups : 0;
     const hc128 z = ctx->znodes[k], w = ctx->zweights[k];
     node_coefs(ctx, z, coef);
     for (int j = 0; j < m; ++j)
@@ -1345,9 +1390,10 @@ static int contour_node(feast_ctx* ctx, int k, const feast_c128* lambda, int fir
     CUDA_TRY(ctx, cudaMemcpyAsync(d_d, d.data(), sizeof(c128) * m, cudaMemcpyHostToDevice, ctx->stream));
     cudaEventRecord(e0, ctx->stream);
     int j0 = 0, mloc = m;
-    if (ctx->col_shard) {   // this rank's column slice of the right-hand side, as a compact block
-        j0 = (int)((int64_t)ctx->rank * m / ctx->nranks);
-        mloc = (int)((int64_t)(ctx->rank + 1) * m / ctx->nranks) - j0;
+    if (ctx->col_shard && ctx->ngroups < ctx->nranks) {   // this rank's column slice of the right-hand side, as a compact block
+        const int gs = ctx->nranks / ctx->ngroups, sl = ctx->rank % gs;
+        j0 = (int)((int64_t)sl * m / gs);
+        mloc = (int)((int64_t)(sl + 1) * m / gs) - j0;
         FEAST_TRY(launch_gather_cols(ctx, n, m, j0, mloc, rhs, ctx->W2.p));
         rhs = ctx->W2.p;
     }
@@ -1381,7 +1427,7 @@ static int contour_end(feast_ctx* ctx, int solver, feast_stats& st) {
     if (ctx->nranks > 1) {                                                                     // NC1
         const NcclApi* api = nccl_api();
         cudaEvent_t e0 = ctx->evn[0], e3 = ctx->evn[3];
-        const bool can_move_nodes = contour_can_move_nodes(ctx, solver);
+        const bool can_move_nodes = contour_can_move_nodes(ctx, solver) || (ctx->col_shard && ctx->auto_balance);
         cudaEventRecord(e0, ctx->stream);
         (void)nep;
         int rc = 0;
@@ -1395,6 +1441,7 @@ static int contour_end(feast_ctx* ctx, int solver, feast_stats& st) {
             rc = api->AllReduce(cbuf, cbuf, (size_t)nnodes, kNcclDouble, kNcclSum, ctx->nccl_comm, ctx->stream);
             if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclAllReduce (node costs) failed");
             CUDA_TRY(ctx, cudaMemcpyAsync(ctx->node_cost.data(), cbuf, sizeof(double) * nnodes, cudaMemcpyDeviceToHost, ctx->stream));
+            // (column mode: the sum runs over the nranks / ngroups ranks of a node's group, all at the same slice width)
         }
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         if (can_move_nodes) ctx->have_costs = true;
@@ -1426,7 +1473,7 @@ int feast_contour_apply(feast_ctx* ctx, const feast_c128* lambda, int first_pass
     FEAST_TRY(contour_begin(ctx, solver));
     const int nnodes = (int)ctx->znodes.size();
     for (int k = 0; k < nnodes; ++k) {
-        if (!ctx->col_shard && ctx->owner[k] != ctx->rank) continue;
+        if (!contour_my_node(ctx, k)) continue;
         FEAST_TRY(contour_node(ctx, k, lambda, first_pass, solver, method, st, &rc_final));
     }
     FEAST_TRY(contour_end(ctx, solver, st));

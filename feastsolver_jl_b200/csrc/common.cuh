@@ -175,6 +175,8 @@ struct feast_ctx {
     std::vector<double> last_fro;       // ||T(l_j)||_F of the last polynomial residual
     int shard_mode = FEAST_SHARD_AUTO;  // multi-GPU sharding axis of the contour loop
     bool col_shard = false;             // the running pass shards right-hand-side columns instead of nodes
+    int ngroups = 1;                    // column mode: rank groups (a node belongs to one group, see choose_groups in api.cu)
+    std::vector<int> gowner;            // column mode: node -> group
     BlockVec Ql, Xl, Rl;                // left subspace of the two-sided driver (dual_gen_feast!)
     BlockVec kx, kr, kp, kq, ks, kt, kv, krh; // Krylov work
     c128* gm_V = nullptr;         // GMRES basis: (gm_restart + 1) blocks

@@ -92,7 +92,8 @@ int amg_build(feast_ctx* ctx, int64_t n, const int64_t* rowptr, const int* col, 
               const std::vector<int>& order, const std::vector<int>& dpos0, std::string* why);
 void amg_free(feast_ctx* ctx);
 int amg_ensure_blocks(feast_ctx* ctx);
-int amg_assemble(feast_ctx* ctx, const hc128* coef, const c128* zvals0, int* info);
+int amg_assemble(feast_ctx* ctx, const hc128* coef, const c128* zvals0, int node, int* info);   // node >= 0: cache the coarse inverse
+void amg_drop_cache(feast_ctx* ctx);
 int amg_apply(feast_ctx* ctx, const c128* zvals0, const c128* r, c128* y, c128* t, c128** out, c128* dot_rz, bool* dot_done);
 int amg_info(const feast_ctx* ctx, int* nlevels, int* sizes, int cap, double* setup_seconds);
 

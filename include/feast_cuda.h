@@ -90,7 +90,8 @@ typedef struct {
     double t_spmm_ms;         /* Krylov: device time inside the SpMM launches       */
     int64_t spmm_launches;    /* Krylov: number of SpMM launches                    */
     int    precond_levels;    /* levels of the multigrid preconditioner in use (0: unpreconditioned) */
-    int    col_sharded;       /* 1: this pass sharded right-hand-side COLUMNS over the ranks (every rank ran all nodes) */
+    int    col_sharded;       /* 0: nodes sharded over the ranks; s >= 1: column mode, every node ran on s ranks (a group),
+                                 each solving m0 / s of its right-hand-side columns                              */
 } feast_stats;
 
 /* ---- library / context ---------------------------------------------- */
