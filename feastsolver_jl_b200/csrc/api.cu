@@ -1112,6 +1112,25 @@ int feast_comm_init(feast_ctx* ctx, int nranks, int rank, const void* id128) {
         memcpy(&id, id128, sizeof(id));
         int rc = api->CommInitRank(&ctx->nccl_comm, nranks, id, rank);
         if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclCommInitRank: %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
+        // NCCL sets up its channels / peer connections lazily at the first collective (seconds at 8 ranks): do that here,
+        // on a private stream and with a message large enough to take the bandwidth algorithm of the real all-reduce, so
+        // that it overlaps the host-side layout build (the binding runs this entry on a helper thread) instead of
+        // landing inside the first contour pass.
+        static const bool warm = !(getenv("FEAST_NCCL_WARMUP") && atoi(getenv("FEAST_NCCL_WARMUP")) == 0);
+        if (warm) {
+            cudaStream_t ws = nullptr;
+            double* buf = nullptr;
+            const size_t count = (size_t)8 << 20;   // 64 MB
+            if (cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking) == cudaSuccess && cudaMalloc((void**)&buf, count * sizeof(double)) == cudaSuccess) {
+                cudaMemsetAsync(buf, 0, count * sizeof(double), ws);
+                rc = api->AllReduce(buf, buf, count, kNcclDouble, kNcclSum, ctx->nccl_comm, ws);
+                cudaStreamSynchronize(ws);
+            }
+            if (buf) cudaFree(buf);
+            if (ws) cudaStreamDestroy(ws);
+            cudaGetLastError();
+            if (rc) return feast_fail(ctx, FEAST_ERR_NCCL, "ncclAllReduce (warm-up): %s", api->GetErrorString ? api->GetErrorString(rc) : "error");
+        }
     }
     for (size_t k = 0; k < ctx->owner.size(); ++k) ctx->owner[k] = (int)(k % nranks);
     return 0;

@@ -490,6 +490,8 @@ def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, 
                 rec.update(st)
                 tick("contour_passes_s")
                 ph.setdefault("contour_pass_s", []).append(st["t_total_ms"] / 1e3)
+                ph.setdefault("contour_pass_allreduce_s", []).append(st["t_reduce_ms"] / 1e3)
+                ph.setdefault("contour_pass_col_slices", []).append(st.get("col_sharded", 0))
             hist.append(rec)
         X[:, :] = ctx.get_X()
         tick("download_s")
