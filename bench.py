@@ -377,7 +377,7 @@ def run_ours(args):
                 "api": "feastsolver_jl_b200.gen_feast(X, A, B, contour) with host numpy/scipy buffers, to convergence",
                 "phases_rank0_s": phases, "phases_max_over_ranks_s": phases_max,
                 "preconditioner_setup_s": st_e2e["preconditioner"]["setup_s"]},
-        "gpu_launches": launches,
+        "gpu_launches": launches, "host_cpus": os.cpu_count(),
         "roofline": {"kernel": "spmm_tiled_kernel<c128, DOT> (COCG q = (A - zB) p, fused <p,q>)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,

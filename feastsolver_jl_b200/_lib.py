@@ -113,6 +113,7 @@ SIGNATURES = {
     "feast_debug_amg_level_info": (_i, [_vp, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_double)]),
     "feast_debug_amg_level_get": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "feast_debug_amg_free": (None, [_vp]),
+    "feast_debug_pick_groups": (_i, [_i, _vp, _i, _i, _vp]),
     "feast_debug_cholqr": (_i, [_i64, _i, _vp, _i64, _vp, C.POINTER(_i)]),
     "feast_debug_tile_plan": (_i, [_i64, _vp, _vp, _i, _i, _i, _i, _i, _vp, C.POINTER(_i), C.POINTER(C.c_double)]),
 }

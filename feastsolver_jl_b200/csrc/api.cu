@@ -598,32 +598,40 @@ void rebalance_nodes(feast_ctx* ctx) {
 // measured in the previous pass every divisor G of nranks is scored by
 //     (LPT makespan over G groups) x (columns per rank + fixed), fixed = 12 columns (FEAST_SHARD_FIXED_COLS)
 // and the best one is taken; identical on every rank (the cost vector is all-reduced).
-void choose_groups(feast_ctx* ctx) {
-    static const double fixed_cols = getenv("FEAST_SHARD_FIXED_COLS") ? atof(getenv("FEAST_SHARD_FIXED_COLS")) : 12.0;
-    static const int forced = getenv("FEAST_SHARD_GROUPS") ? atoi(getenv("FEAST_SHARD_GROUPS")) : 0;
-    const int nn = (int)ctx->znodes.size(), nr = ctx->nranks;
-    ctx->ngroups = 1;
-    ctx->gowner.assign(nn, 0);
-    if (!ctx->have_costs && !forced) return;
+int pick_groups(int nn, const double* cost, int nr, int m0, double fixed_cols, int forced, std::vector<int>& gowner) {
     std::vector<int> order(nn);
     for (int k = 0; k < nn; ++k) order[k] = k;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ctx->node_cost[a] > ctx->node_cost[b]; });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
     double best = -1.0;
+    int bestG = 1;
+    gowner.assign(nn, 0);
     for (int G = 1; G <= nr; ++G) {
         if (nr % G != 0 || (forced && G != forced)) continue;
         const int gs = nr / G;
-        if (ctx->m0 < 2 * gs && gs > 1) continue;
+        if (m0 < 2 * gs && gs > 1) continue;
         std::vector<double> load(G, 0.0);
         std::vector<int> own(nn, 0);
         for (int k : order) {
             int b = 0;
             for (int g = 1; g < G; ++g) if (load[g] < load[b]) b = g;
             own[k] = b;
-            load[b] += ctx->have_costs ? ctx->node_cost[k] : 1.0;
+            load[b] += cost[k];
         }
-        const double score = *std::max_element(load.begin(), load.end()) * ((double)ctx->m0 / gs + fixed_cols);
-        if (best < 0.0 || score < best) { best = score; ctx->ngroups = G; ctx->gowner = own; }
+        const double score = *std::max_element(load.begin(), load.end()) * ((double)m0 / gs + fixed_cols);
+        if (best < 0.0 || score < best) { best = score; bestG = G; gowner = own; }
     }
+    return bestG;
+}
+
+void choose_groups(feast_ctx* ctx) {
+    static const double fixed_cols = getenv("FEAST_SHARD_FIXED_COLS") ? atof(getenv("FEAST_SHARD_FIXED_COLS")) : 12.0;
+    static const int forced = getenv("FEAST_SHARD_GROUPS") ? atoi(getenv("FEAST_SHARD_GROUPS")) : 0;
+    const int nn = (int)ctx->znodes.size();
+    ctx->ngroups = 1;
+    ctx->gowner.assign(nn, 0);
+    if (!ctx->have_costs && !forced) return;
+    std::vector<double> unit(nn, 1.0);
+    ctx->ngroups = pick_groups(nn, ctx->have_costs ? ctx->node_cost.data() : unit.data(), ctx->nranks, ctx->m0, fixed_cols, forced, ctx->gowner);
 }
 
 // W = op(slot)^H * V.  Dense: one DMMA GEMM on the conjugate-transposed view.  Sparse: supported when
@@ -1005,6 +1013,15 @@ int feast_set_mixed_precision(feast_ctx* ctx, int on) {
     ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
     ctx->mixed_prec = on ? 1 : 0;
     return 0;
+}
+
+// host-only: the group choice of the column-sharded contour loop for given node costs (CPU tests of the N > 1 logic)
+int feast_debug_pick_groups(int nnodes, const double* cost, int nranks, int m0, int* group_of_node) {
+    if (nnodes < 1 || !cost || nranks < 1 || m0 < 1 || !group_of_node) return -1;
+    std::vector<int> own;
+    const int G = pick_groups(nnodes, cost, nranks, m0, 12.0, 0, own);
+    for (int k = 0; k < nnodes; ++k) group_of_node[k] = own[k];
+    return G;
 }
 
 int feast_set_sharding(feast_ctx* ctx, int mode) {

@@ -261,6 +261,8 @@ FEAST_API int  feast_debug_amg_level_info(const void* handle, int lev, int* n, i
 FEAST_API int  feast_debug_amg_level_get(const void* handle, int lev, int* rowptr, int* col, double* vals_flat,
                                          int* p_rowptr, int* p_col, double* p_val);
 FEAST_API void feast_debug_amg_free(void* handle);
+/* host-only: rank groups of the column-sharded contour loop for given node costs; returns the number of groups */
+FEAST_API int  feast_debug_pick_groups(int nnodes, const double* cost, int nranks, int m0, int* group_of_node);
 FEAST_API int  feast_debug_cholqr(int64_t n, int m, feast_c128* V, int64_t ldv, feast_c128* Rtot, int* passes);
 
 #ifdef __cplusplus

@@ -265,3 +265,22 @@ def test_column_slices_partition_the_columns():
             assert sl[0][0] == 0 and sl[-1][1] == m0
             assert all(sl[i][1] == sl[i + 1][0] for i in range(nr - 1))
             assert max(b - a for a, b in sl) - min(b - a for a, b in sl) <= 1
+
+
+def test_group_choice_of_the_column_sharded_loop(lib):
+    """csrc/api.cu pick_groups: G rank groups (nodes -> groups by LPT on the measured costs) x nranks/G column slices,
+    scored by makespan x (columns per rank + 12).  With the iteration counts measured on the C2 pencil (near-axis nodes
+    ~12x the others) 8 ranks take 4 groups x 2 slices, 2 ranks take 2 groups (pure node sharding), equal costs keep
+    one group (pure column split)."""
+    from feastsolver_jl_b200 import _lib
+    cost = np.array([126, 52, 25, 16, 12, 11, 10, 10] * 2, dtype=np.float64)
+    own = np.zeros(16, dtype=np.int32)
+    G = lib.feast_debug_pick_groups(16, _lib.ptr(cost), 8, 64, _lib.ptr(own))
+    assert G == 4
+    loads = np.bincount(own, weights=cost, minlength=G)
+    assert loads.max() <= 1.1 * cost.sum() / G and set(own) == set(range(G))
+    assert lib.feast_debug_pick_groups(16, _lib.ptr(cost), 2, 64, _lib.ptr(own)) == 2
+    flat = np.ones(16)
+    assert lib.feast_debug_pick_groups(16, _lib.ptr(flat), 8, 64, _lib.ptr(own)) in (4, 8)   # balanced either way: widest slices win
+    one = np.array([100.0] + [1.0] * 15)
+    assert lib.feast_debug_pick_groups(16, _lib.ptr(one), 8, 64, _lib.ptr(own)) == 1           # one dominant node: split its columns
