@@ -25,7 +25,7 @@ exact = wl.laplacian3d_spectrum(m); exact = exact[np.abs(exact - c) <= r]
 ok = e.size == exact.size and np.abs(np.sort(e.real) - exact).max() < 1e-10 * exact.max() and res.max() < 1e-11
 nodes_local = st["history"][0].get("nodes_local")
 col_sharded = st["history"][0].get("col_sharded")
-ok = ok and col_sharded == world and nodes_local == 16        # AUTO, first pass: pure column split, all nodes on every rank
+ok = ok and col_sharded >= 1 and 1 <= nodes_local <= 16       # AUTO (Krylov): rank groups x column slices of the right-hand sides
 stn = {}
 en, vn, resn = fs.gen_feast(X0.copy(), A, B, ct, eps=1e-12, iter=10, solver_opts=dict(opts, shard=_lib.SHARD_NODES), stats=stn,
                             comm=make_comm_hook())
