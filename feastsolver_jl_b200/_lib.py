@@ -107,6 +107,7 @@ SIGNATURES = {
     "feast_phase_times": (_i, [_vp, _vp, _i]),
     "feast_set_mixed_precision": (_i, [_vp, _i]),
     "feast_set_preconditioner": (_i, [_vp, _i]),
+    "feast_set_preconditioner_shift": (_i, [_vp, _d]),
     "feast_preconditioner_info": (_i, [_vp, C.POINTER(_i), _vp, _i, C.POINTER(C.c_double)]),
     "feast_layout_info": (_i, [_vp, _vp, C.POINTER(C.c_double)]),
     "feast_debug_amg_build": (_vp, [_i64, _vp, _vp, _i, _vp, _i, C.POINTER(_i), C.POINTER(C.c_double)]),

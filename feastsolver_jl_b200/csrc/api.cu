@@ -94,6 +94,7 @@ void free_pattern(feast_ctx* ctx) {
     ctx->tiles_ok = false;
     ctx->ntiles = 0;
     dev_free(ctx->zvals);
+    dev_free(ctx->zvals_pc);
     for (int i = 0; i < FEAST_MAX_SLOTS; ++i) { dev_free(ctx->ops[i].uvals_r); dev_free(ctx->ops[i].uvals_c); }
 }
 
@@ -673,10 +674,26 @@ int krylov_any(feast_ctx* ctx, int method, const hc128* coef, const c128* zvals,
                feast_stats* st, int node = -1) {
     if (ctx->amg && method == FEAST_KRYLOV_COCG && !ctx->mixed_prec) {
         int info = 0;
-        FEAST_TRY(amg_assemble(ctx, coef, zvals, node, &info));
+        // Complex-shifted preconditioner (the "shifted Laplacian" idea): the hierarchy is assembled for
+        // z~ = z + i beta |z| sign(Im z) instead of z.  For shifts inside the spectrum (interior slices: many eigenmodes
+        // below Re z that the coarse levels no longer resolve) the cycle for the damped operator is a much better
+        // preconditioner of the true one (numpy prototype at 40^3, third slice: 1041 -> 372 iterations on the worst node);
+        // for the lowest slice beta = 0 is best.  coef[1] carries -z for the linear problems this path serves.
+        const c128* zpc = zvals;
+        hc128 cpc[FEAST_MAX_SLOTS];
+        for (int s = 0; s < FEAST_MAX_SLOTS; ++s) cpc[s] = coef[s];
+        if (ctx->precond_shift != 0.0 && ctx->problem != FEAST_PROBLEM_POLYNOMIAL) {
+            const hc128 z = -coef[1] / coef[0];
+            const hc128 zt = z + hc128(0.0, ctx->precond_shift * std::abs(z) * (z.imag() < 0 ? -1.0 : 1.0));
+            cpc[1] = -zt * coef[0];
+            if (!ctx->zvals_pc) FEAST_TRY(dev_alloc(ctx, &ctx->zvals_pc, ctx->unnz));
+            FEAST_TRY(assemble_sparse_Z(ctx, cpc, ctx->zvals_pc));
+            zpc = ctx->zvals_pc;
+        }
+        FEAST_TRY(amg_assemble(ctx, cpc, zpc, node, &info));
         if (info) return feast_fail(ctx, FEAST_ERR_SINGULAR, "zero pivot at column %d of the coarsest multigrid operator", info);
         if (st) amg_info(ctx, &st->precond_levels, nullptr, 0, nullptr);
-        return krylov_solve_pcocg(ctx, zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, kr);
+        return krylov_solve_pcocg(ctx, zvals, zpc, rhs, Y, ctx->inner_tol, ctx->max_inner, kr);
     }
     if (ctx->mixed_prec && method == FEAST_KRYLOV_COCG && (ctx->m0 % 2) == 0 && ctx->m0 <= 128 && ctx->tiles_ok && ctx->tile_cfg == 0)
         return krylov_solve_mixed(ctx, zvals, rhs, Y, ctx->inner_tol, ctx->max_inner, kr);
@@ -1011,6 +1028,15 @@ int feast_set_preconditioner(feast_ctx* ctx, int kind) {
     ARG_CHECK(ctx, kind >= FEAST_PRECOND_NONE && kind <= FEAST_PRECOND_AUTO, 2, "unknown preconditioner kind");
     ctx->precond = kind;
     if (ctx->problem_ready && !ctx->storage_dense && want_amg(ctx) != (ctx->amg != nullptr)) FEAST_TRY(rebuild_layout(ctx));
+    return 0;
+}
+
+// beta of the complex-shifted preconditioner (0: the hierarchy is assembled at the node itself)
+int feast_set_preconditioner_shift(feast_ctx* ctx, double beta) {
+    ARG_CHECK(ctx, ctx != nullptr, 1, "null context");
+    ARG_CHECK(ctx, beta >= 0.0 && beta <= 4.0, 2, "beta must be in [0, 4]");
+    if (beta != ctx->precond_shift) amg_drop_cache(ctx);   // the cached coarse inverses belong to the old shift
+    ctx->precond_shift = beta;
     return 0;
 }
 

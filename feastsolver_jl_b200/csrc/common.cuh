@@ -135,6 +135,8 @@ struct feast_ctx {
     uint16_t* u_lcol = nullptr;   // [unnz] tile-local column numbers (own rows, then the halo list)
     double halo_ratio = 0.0;      // halo rows per row (diagnostic)
     c128* zvals = nullptr;        // assembled shifted operator on the union pattern
+    c128* zvals_pc = nullptr;     // ... at the preconditioner's shift (complex-shifted multigrid, precond_shift != 0)
+    double precond_shift = 0.0;   // beta: the multigrid hierarchy is assembled at z + i beta |z| sign(Im z)
     c128* zdense = nullptr;       // assembled dense shifted operator (n x n col-major)
     int*  zpiv = nullptr;
     c128* zdinv = nullptr;        // diagonal-block inverses of the scratch factorisation

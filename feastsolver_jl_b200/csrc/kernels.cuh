@@ -82,7 +82,8 @@ int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs,
 // EXPERIMENTAL: COCG with complex64 storage of the Krylov blocks (mixed_prec); needs m0 even and the default tile plan
 int krylov_solve_mixed(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out);
 // COCG preconditioned by the smoothed-aggregation V-cycle (needs ctx->amg assembled for the node)
-int krylov_solve_pcocg(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out);
+int krylov_solve_pcocg(feast_ctx* ctx, const c128* zvals, const c128* zvals_pc, const c128* Rhs, c128* Y, double tol, int maxit,
+                       KrylovResult* out);
 int krylov_kernel_bench(feast_ctx* ctx, int which, int reps, float* ms);
 int gmres_solve(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out);
 size_t gmres_small_bytes(int m, int R);

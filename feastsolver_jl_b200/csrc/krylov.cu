@@ -501,7 +501,9 @@ int krylov_kernel_bench(feast_ctx* ctx, int which, int reps, float* ms) {
 // (unconjugated bilinear forms throughout).  Per iteration: one fine SpMM for q, one V-cycle (two fine SpMMs plus the
 // coarse levels) and 3 + 1 + 5 block passes of vector work; on the C2 pencil it needs ~10x fewer iterations than
 // the plain recurrence (numpy prototype of the same cycle: 262 instead of 2831 over the 8 upper nodes at 64^3).
-int krylov_solve_pcocg(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out) {
+// zvals: the operator of the system; zvals_pc: the operator the cycle smooths with (== zvals unless the preconditioner is shifted)
+int krylov_solve_pcocg(feast_ctx* ctx, const c128* zvals, const c128* zvals_pc, const c128* Rhs, c128* Y, double tol, int maxit,
+                       KrylovResult* out) {
     const int64_t n = ctx->n;
     const int m = ctx->m0;
     const int64_t total = n * m;
@@ -528,7 +530,7 @@ int krylov_solve_pcocg(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128*
     auto precondition = [&](c128* dot_out) -> int {
         c128* zr = nullptr;
         bool dot_done = false;
-        FEAST_TRY(amg_apply(ctx, zvals, r, z, t, &zr, dot_out, &dot_done));
+        FEAST_TRY(amg_apply(ctx, zvals_pc, r, z, t, &zr, dot_out, &dot_done));
         if (zr != z) std::swap(z, t);
         if (!dot_done) FEAST_TRY(launch_coldot(ctx, n, m, r, z, false, dot_out));
         return 0;

@@ -108,9 +108,11 @@ class FeastContext:
         self._ck(self.lib.feast_set_contour(self.h, len(z), _lib.ptr(z), _lib.ptr(w)))
 
     def set_solver(self, kind=_lib.SOLVER_AUTO, krylov=_lib.KRYLOV_AUTO, inner_tol=1e-8, max_inner=4000, store=False, precond=None,
-                   shard=None):
+                   shard=None, precond_shift=None):
         if precond is not None:   # before set_solver: one layout rebuild at most
             self.set_preconditioner(precond)
+        if precond_shift is not None:
+            self._ck(self.lib.feast_set_preconditioner_shift(self.h, float(precond_shift)))
         if shard is not None:
             self.set_sharding(shard)
         self._ck(self.lib.feast_set_solver(self.h, kind, krylov, float(inner_tol), int(max_inner), int(bool(store))))

@@ -236,6 +236,9 @@ FEAST_API int  feast_phase_times(feast_ctx* ctx, double* ms3, int reset);
 FEAST_API int  feast_set_mixed_precision(feast_ctx* ctx, int on);
 /* kind: FEAST_PRECOND_*.  Takes effect immediately (the device layout is rebuilt if a hierarchy has to be added or dropped). */
 FEAST_API int  feast_set_preconditioner(feast_ctx* ctx, int kind);
+/* complex-shifted preconditioner: the hierarchy is assembled at z + i*beta*|z|*sign(Im z) instead of the node z
+ * (beta = 0 default; ~0.5 for contours in the interior of the spectrum) */
+FEAST_API int  feast_set_preconditioner_shift(feast_ctx* ctx, double beta);
 /* levels in use (0 = none), their sizes (up to cap entries) and the host setup time of the hierarchy */
 FEAST_API int  feast_preconditioner_info(const feast_ctx* ctx, int* nlevels, int* sizes, int cap, double* setup_seconds);
 /* Internal layout of the sparse path (no reference counterpart: UMFPACK reorders internally as

@@ -17,6 +17,9 @@ ap.add_argument("--slices", type=int, default=None)
 ap.add_argument("--target", type=int, default=36)
 ap.add_argument("--m0", type=int, default=64)
 ap.add_argument("--tol", type=float, default=1e-5)
+ap.add_argument("--precond-shift", type=float, default=0.5,
+                help="beta of the complex-shifted multigrid preconditioner for the INTERIOR slices (slice 0 uses 0)")
+ap.add_argument("--only", type=int, nargs="*", default=None, help="run these slice indices only")
 a = ap.parse_args()
 world = int(os.environ.get("WORLD_SIZE", "1"))
 rank = int(os.environ.get("RANK", "0"))
@@ -34,7 +37,7 @@ for s in range(nslices):
     c, r, cnt = wl.c2_slice(a.grid, target=a.target, first=first)
     bounds.append((c, r, cnt, first))
     first += cnt
-mine = [s for s in range(nslices) if s % world == rank]
+mine = [s for s in range(nslices) if s % world == rank and (a.only is None or s in a.only)]
 found, t_my, res_max, ok = 0, 0.0, 0.0, True
 lam_all = wl.laplacian3d_spectrum(a.grid, count=first + 16)
 for s in mine:
@@ -43,7 +46,8 @@ for s in mine:
     X0 = wl.rand_subspace(n, a.m0, seed=100 + s)
     t0 = time.perf_counter()
     e, v, res = fs.gen_feast(X0, A, B, ct, eps=1e-12, iter=10,
-                             solver_opts={"kind": _lib.SOLVER_KRYLOV, "inner_tol": a.tol, "max_inner": 8000},
+                             solver_opts={"kind": _lib.SOLVER_KRYLOV, "inner_tol": a.tol, "max_inner": 8000,
+                                          "precond_shift": a.precond_shift if s > 0 else 0.0},
                              ctx=fs.FeastContext(device=local))
     t_my += time.perf_counter() - t0
     exact = lam_all[f0:f0 + cnt]
@@ -54,7 +58,7 @@ for s in mine:
     found += int(ec.size)
     res_max = max(res_max, float(res[conv].max()) if conv.any() else 0.0)
     print(f"[rank {rank}] slice {s}: c={c:.5f} r={r:.5f} expected {cnt} returned {e.size} converged {ec.size} "
-          f"ok={this_ok} time {time.perf_counter() - t0:.1f}s", file=sys.stderr, flush=True)
+          f"ok={this_ok} time {time.perf_counter() - t0:.1f}s precond_shift={a.precond_shift if s > 0 else 0.0}", file=sys.stderr, flush=True)
 if world > 1:
     t = torch.tensor([float(found), t_my, res_max, 0.0 if ok else 1.0], dtype=torch.float64, device="cuda")
     tsum, tmax = t.clone(), t.clone()
