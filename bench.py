@@ -494,8 +494,12 @@ def run_c3(args):
                                   f"{nodes} trapezoid nodes sharded over {world} GPU(s), feast! with store=true; step = one outer "
                                   f"iteration ({nodes} node solves; the {nodes} LU factorisations happen in the first one)",
                       "l2_policy": "operands (4.3 GB per matrix) exceed the 126 MB L2"},
-           "time_to_solution_s": tts, "outer_iterations": len(st["history"]), "eigenvalues_found": int(e.size),
-           "max_residual": float(res.max()) if res.size else None,
+           # feast! returns every Ritz value inside the contour, spurious ones included (src/feast.jl:77-79): with m0 = 128 > #eigenvalues
+           # one or two of them wander through the contour, which is also why the run uses all 10 iterations (feast.jl:53 looks at the
+           # maximum over everything inside).  The converged pairs are the ones with a small residual.
+           "time_to_solution_s": tts, "outer_iterations": len(st["history"]), "ritz_values_inside": int(e.size),
+           "eigenvalues_found": int((res < 1e-9).sum()), "max_residual": float(res[res < 1e-9].max()) if (res < 1e-9).any() else None,
+           "max_residual_all_inside": float(res.max()) if res.size else None,
            "e2e": {"value": nodes * steps / tts, "unit": "node_solves/s", "h2d_bytes_per_step": int((A.nbytes + X0.nbytes) / max(1, steps)),
                    "d2h_bytes_per_step": int(X0.nbytes / max(1, steps)), "time_to_solution_s": tts,
                    "api": "feastsolver_jl_b200.feast(X, A; nodes, c, r, store=true) with host numpy buffers, to convergence",
