@@ -541,7 +541,7 @@ def main():
     ap.add_argument("--precond", default="auto", choices=["auto", "none", "amg"],
                     help="Krylov preconditioner (auto: smoothed-aggregation V-cycle when applicable)")
     ap.add_argument("--mixed-prec", action="store_true",
-                    help="EXPERIMENTAL: complex64 storage of the COCG blocks in the steady-state leg (not the headline configuration)")
+                    help="mixed_prec: complex64 storage of the COCG blocks, unpreconditioned recurrence (not the headline configuration)")
     args = ap.parse_args()
     args.grid_given = args.grid is not None
     if args.grid is None:

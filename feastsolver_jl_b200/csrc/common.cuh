@@ -158,7 +158,7 @@ struct feast_ctx {
     int precond = FEAST_PRECOND_AUTO;   // Krylov preconditioner request (feast_set_preconditioner)
     AmgDev* amg = nullptr;        // smoothed-aggregation hierarchy (built with the union pattern when applicable)
     std::string amg_why;          // why no hierarchy was built (diagnostic)
-    int mixed_prec = 0;           // EXPERIMENTAL: complex64 storage of the COCG blocks (feast_set_mixed_precision)
+    int mixed_prec = 0;           // mixed_prec: complex64 storage of the COCG blocks (feast_set_mixed_precision)
     std::vector<DenseLU> stored;  // per node (only local nodes populated)
     std::vector<BandFactor> bstored; // per node, banded solver
     BandFactor bscratch;          // store=0

@@ -79,7 +79,7 @@ struct KrylovResult { int iters; double relres_max; bool converged; double spmm_
 int krylov_solve(feast_ctx* ctx, int method, const c128* zvals, const c128* Rhs, c128* Y,
                  double tol, int maxit, KrylovResult* out);
 
-// EXPERIMENTAL: COCG with complex64 storage of the Krylov blocks (mixed_prec); needs m0 even and the default tile plan
+// COCG with complex64 storage of the Krylov blocks (mixed_prec); needs m0 even and the default tile plan
 int krylov_solve_mixed(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, double tol, int maxit, KrylovResult* out);
 // COCG preconditioned by the smoothed-aggregation V-cycle (needs ctx->amg assembled for the node)
 int krylov_solve_pcocg(feast_ctx* ctx, const c128* zvals, const c128* zvals_pc, const c128* Rhs, c128* Y, double tol, int maxit,

@@ -582,12 +582,13 @@ int krylov_solve_pcocg(feast_ctx* ctx, const c128* zvals, const c128* zvals_pc, 
     return 0;
 }
 
-// =============================================================================== mixed-precision COCG (EXPERIMENTAL)
+// =============================================================================== mixed-precision COCG
 // The reference's `mixed_prec=true` (src/feast.jl:19-25: ComplexF32 factorisation and solve inside the double-precision
 // RII loop) on the Krylov path: the four COCG blocks (x, r, p, q) are STORED in complex64, which halves the HBM traffic
 // of every kernel of the iteration; all arithmetic (products, axpys, dots, the per-column recurrences) is done in double
 // on the loaded values.  The attainable inner residual is limited by the complex64 rounding of r (~1e-6 relative), the
-// outer RII loop corrects in double.  NOT YET RUN ON A GPU (written after the round's GPU budget was spent).
+// outer RII loop corrects in double.  Measured on the C2 pencil (round 2): the iteration is 1.6x faster, 45 % more
+// iterations are needed (the rounded recurrences lose Krylov orthogonality earlier): 1.12x per outer iteration.
 namespace {
 
 typedef float2 c64;

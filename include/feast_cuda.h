@@ -229,10 +229,10 @@ FEAST_API int  feast_timer_stop(feast_ctx* ctx, float* ms);
 FEAST_API int64_t feast_launch_count(const feast_ctx* ctx);
 /* device-timed phases since the last reset (ms): [0]=project [1]=recover [2]=contour_apply */
 FEAST_API int  feast_phase_times(feast_ctx* ctx, double* ms3, int reset);
-/* EXPERIMENTAL (written after the round's GPU budget was spent, not yet run on a GPU): the reference's
- * `mixed_prec=true` (src/feast.jl:19-25, ComplexF32 solves inside the double-precision RII loop) for the
- * Krylov path: the COCG blocks are stored in complex64 (half the HBM traffic), arithmetic stays double.
- * Applies when the inner solver is COCG, m0 is even and the default tile plan is in use; ignored otherwise. */
+/* The reference's `mixed_prec=true` (src/feast.jl:19-25, ComplexF32 solves inside the double-precision RII loop) for the
+ * Krylov path: the COCG blocks are stored in complex64 (half the HBM traffic), arithmetic stays double; the recurrence is
+ * the unpreconditioned one.  Applies when the inner solver is COCG, m0 is even and the default tile plan is in use;
+ * ignored otherwise.  (Validated on a B200 in round 2: tests/test_gpu_parity.py::test_feast_mixed_prec_krylov.) */
 FEAST_API int  feast_set_mixed_precision(feast_ctx* ctx, int on);
 /* kind: FEAST_PRECOND_*.  Takes effect immediately (the device layout is rebuilt if a hierarchy has to be added or dropped). */
 FEAST_API int  feast_set_preconditioner(feast_ctx* ctx, int kind);
