@@ -213,14 +213,15 @@ void amg_free(feast_ctx* ctx) {
     ctx->amg = nullptr;
 }
 
-// Build the hierarchy from the natural-order union pattern and upload it.  `order` (new -> old, may be empty) is the
-// row renumbering of the device layout of level 0; dpos0 = diagonal positions in the (padded) device layout.
-int amg_build(feast_ctx* ctx, int64_t n, const int64_t* rowptr, const int* col, int nslots, const double* const* vals,
-              const std::vector<int>& order, const std::vector<int>& dpos0, std::string* why) {
+int amg_max_coarse() {
+    static const int v = getenv("FEAST_AMG_COARSE") ? atoi(getenv("FEAST_AMG_COARSE")) : 4096;
+    return v;
+}
+
+// Upload a hierarchy built by amg_setup_host from the natural-order union pattern.  `order` (new -> old, may be empty) is
+// the row renumbering of the device layout of level 0; dpos0 = diagonal positions in the (padded) device layout.
+int amg_build(feast_ctx* ctx, AmgHost& H, int nslots, const std::vector<int>& order, const std::vector<int>& dpos0, std::string* why) {
     amg_free(ctx);
-    static const int max_coarse = getenv("FEAST_AMG_COARSE") ? atoi(getenv("FEAST_AMG_COARSE")) : 4096;
-    AmgHost H;
-    amg_setup_host(n, rowptr, col, nslots, vals, max_coarse, H);
     if (!H.ok) { if (why) *why = H.why; return 0; }
     AmgDev* A = new AmgDev();
     ctx->amg = A;

@@ -89,8 +89,9 @@ int gmres_solve(feast_ctx* ctx, const c128* zvals, const c128* Rhs, c128* Y, dou
 size_t gmres_small_bytes(int m, int R);
 
 // ---- amg.cu: smoothed-aggregation preconditioner of the Krylov inner solves
-int amg_build(feast_ctx* ctx, int64_t n, const int64_t* rowptr, const int* col, int nslots, const double* const* vals,
-              const std::vector<int>& order, const std::vector<int>& dpos0, std::string* why);
+struct AmgHost;
+int amg_max_coarse();
+int amg_build(feast_ctx* ctx, AmgHost& H, int nslots, const std::vector<int>& order, const std::vector<int>& dpos0, std::string* why);
 void amg_free(feast_ctx* ctx);
 int amg_ensure_blocks(feast_ctx* ctx);
 int amg_assemble(feast_ctx* ctx, const hc128* coef, const c128* zvals0, int node, int* info);   // node >= 0: cache the coarse inverse
