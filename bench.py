@@ -358,7 +358,8 @@ def run_ours(args):
                                     + "/".join(str(v) for v in pinfo["sizes"]) if pinfo["levels"] else "")
                                     + f", rel tol {INNER_TOL}" + (", complex64 blocks (mixed_prec)" if args.mixed_prec else "")),
                    "timed_steps": "real pre-convergence passes only (solve restarted from X0 when it converges inside the "
-                                  f"timed region; {restarts} restart(s))",
+                                  f"timed region; {restarts} restart(s)); per-node coarse multigrid inverses are cached after the first pass "
+                                  "of a contour, as in passes 2+ of a solve (the e2e figure includes computing them)",
                    "l2_policy": "inputs (5 GB of Krylov blocks) exceed the 126 MB L2",
                    "sharding": (f"{world // col_sharded} node group(s) x {col_sharded} column slice(s) of the right-hand sides "
                                 "(groups chosen from the measured node costs)" if col_sharded else "contour nodes") if world > 1 else "single GPU",
