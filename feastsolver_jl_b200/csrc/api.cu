@@ -790,7 +790,7 @@ int solve_shifted(feast_ctx* ctx, int solver, int method, int k, const hc128* co
                 return feast_fail(ctx, FEAST_ERR_STATE, "adjoint Krylov solve needs symmetric operators: pass them dense");
             FEAST_TRY(ensure_block(ctx, ctx->W2));
             FEAST_TRY(launch_conj(ctx, n * m, rhs, ctx->W2.p));
-            FEAST_TRY(krylov_any(ctx, method, coef, ctx->zvals, ctx->W2.p, Y, &kr, &st));   // same Z, conjugated data
+            FEAST_TRY(krylov_any(ctx, method, coef, ctx->zvals, ctx->W2.p, Y, &kr, &st, k));   // same Z (and cached coarse inverse), conjugated data
             FEAST_TRY(launch_conj(ctx, n * m, Y, Y));
         } else {
             FEAST_TRY(krylov_any(ctx, method, coef, ctx->zvals, rhs, Y, &kr, &st, k));

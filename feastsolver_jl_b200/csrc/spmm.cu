@@ -190,6 +190,9 @@ int spmm_dispatch(feast_ctx* ctx, int n, int m, const int* rowptr, const int* co
 //   * L2->SM traffic per SpMM = (1 + halo/rows) reads of X; with the tile ordering ~2.1 instead of ~5.5.
 // 2 CTAs of 512 threads per SM: one computes while the other waits for its copies.
 // Measured alternatives at C2 (n = 1e6, m0 = 64, real values 0.515 ms with this kernel):
+//   * (round 2) padding entries predicated off (@P LDS.128) and the row's own x value taken from the diagonal entry instead of
+//     a second load -- 18 % fewer shared-memory wavefronts on paper: 0.78 ms instead of 0.63 ms for the complex + dot variant
+//     (64 registers instead of 58, the extra compares sit in the dependent chain of the loads); reverted;
 //   * 3 or 4 smaller CTAs per SM (TileCfg2 / TileCfg1): 0.510 / 0.505 ms although the halo grows to 1.45 / 1.68;
 //   * one 1024-thread CTA with a ring of 2..4 tile buffers, copies issued one to three passes ahead: 0.70 .. 1.09 ms;
 //   * the same ring fed by four dedicated producer warps (empty/full mbarriers, no CTA barrier): 0.54 ms with per-row
