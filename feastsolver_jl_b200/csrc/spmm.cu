@@ -325,15 +325,9 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
             phase ^= 1u;
 
             const int gg = g < SW ? g : 0;
-            // The kernel is bound by shared-memory bandwidth (ncu: L1/LSU pipe 77 %), so every avoidable wavefront counts:
-            // padding entries issue no load (predicated off), and the row's own x value -- needed by the fused <x, Sx> and by
-            // the post-smoothing epilogue -- is taken from the diagonal entry as it passes by instead of a second load.
-            constexpr bool kNeedOwn = (DOT && EPI == 0) || EPI == 2;
             for (int lr = warp * UPW + sub; lr < rows; lr += NW * UPW) {
                 const int e0 = rs[lr], e1 = rs[lr + 1];
                 c128 acc = cmake(0.0, 0.0);
-                c128 own = cmake(0.0, 0.0);
-                bool have_own = false;
                 for (int e = (dbg & 1) ? e1 : e0; e < e1; e += 8) {
                     // 8 tile-local columns in one 16-byte broadcast load; 0xFFFF = padding (only at the end of a row)
                     const uint4 iv = *reinterpret_cast<const uint4*>(ls + e);
@@ -345,29 +339,24 @@ spmm_tiled_kernel(int m, int ntiles, const int* __restrict__ t_ptr, const int* _
                         if (lc[0] == 0xFFFFu) break;
                         c128 xv[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            xv[k] = cmake(0.0, 0.0);
-                            if (lc[k] != 0xFFFFu) xv[k] = xs[(size_t)lc[k] * SW + gg];
-                            if (kNeedOwn && lc[k] == (unsigned)lr) { own = xv[k]; have_own = true; }
-                        }
+                        for (int k = 0; k < 4; ++k) xv[k] = xs[(size_t)(lc[k] == 0xFFFFu ? (unsigned)lr : lc[k]) * SW + gg];
                         VT vv[4];
                         load_vals4(vs + e + 4 * h, vv);   // padding values are 0
 #pragma unroll
                         for (int k = 0; k < 4; ++k) ValOps<VT>::fma(acc, vv[k], xv[k]);
                     }
                 }
-                if (kNeedOwn && !have_own) own = xs[(size_t)lr * SW + gg];   // no diagonal entry in this row (warp-uniform)
                 if (g < SW && !(dbg & 4)) {
                     if (EPI == 0) {
                         Y[(int64_t)(r0 + lr) * ldy + j0 + g] = acc;
-                        if (DOT) cfma(dacc[s], own, acc);
+                        if (DOT) cfma(dacc[s], xs[(size_t)lr * SW + g], acc);
                     } else {
                         const c128 cv = __ldg(ep.C + (int64_t)(r0 + lr) * ep.ldc + j0 + g);
                         c128 outv = csub(cv, acc);
                         if (EPI == 2) {
                             const c128 wd = cscale(ep.omega, __ldg(ep.dinv + r0 + lr));
                             const c128 resid = outv;
-                            outv = own;
+                            outv = xs[(size_t)lr * SW + g];
                             cfma(outv, wd, resid);
                         }
                         Y[(int64_t)(r0 + lr) * ldy + j0 + g] = outv;
