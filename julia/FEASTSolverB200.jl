@@ -13,7 +13,7 @@ module FEASTSolverB200
 using LinearAlgebra
 using SparseArrays
 
-export feast!, gen_feast!, dual_gen_feast!, nlfeast!, ifeast!, contour_estimate_eig, beyn, block_SS!, nlfeast_moments!
+export feast!, gen_feast!, dual_gen_feast!, nlfeast!, nlfeast_it!, ifeast!, contour_estimate_eig, beyn, block_SS!, nlfeast_moments!
 export in_contour, circular_contour_trapezoidal, circular_contour_gauss,
        rectangular_contour_gauss, rectangular_contour_trapezoidal, rational_func
 export Contour, CircularContour, RectangularContour, CustomContour
@@ -298,6 +298,45 @@ function nlfeast!(T::AbstractVector{<:AbstractMatrix}, X::AbstractMatrix{Complex
             break
         end
         if nit > 1 && sum(res_inside .< spurious) > 0 && maximum(res_inside[res_inside .< spurious]) < ϵ
+            break
+        end
+    end
+    _ck(ctx, ccall((:feast_get_X, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Int64), ctx.h, X, N))
+    finalize(ctx)
+    Λ, X, res
+end
+
+# nlfeast_it!(T, X, nodes, iter; c, r, debug, ϵ)  (src/nlfeast.jl:87-171): nlfeast with INEXACT inner solves -- relative
+# tolerance 1e-3 in the first contour pass (:106), 1e-8 afterwards (:139) -- stopping when max(res[inside]) < ϵ (:164).
+# Krylov inner solves over the tiled SpMM; the warm start `Tinv` of upstream (nodes x N x m0 of storage) is not kept: in
+# residual-inverse-iteration form the right-hand side shrinks with the outer iteration, which plays the same role.
+function nlfeast_it!(T::AbstractVector{<:AbstractMatrix}, X::AbstractMatrix{ComplexF64}, nodes::Integer, iter::Integer;
+                     c=complex(0.0, 0.0), r=1.0, debug=false, ϵ=0.05)
+    N, m₀ = size(X)
+    ctx = FeastCtx()
+    for (i, Ai) in enumerate(T)
+        _set_operator!(ctx, i - 1, Ai, N)
+    end
+    _ck(ctx, ccall((:feast_set_problem, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint), ctx.h, 2, length(T)))
+    contour = circular_contour_trapezoidal(c, r, nodes)
+    z = convert(Vector{ComplexF64}, contour.nodes); w = convert(Vector{ComplexF64}, contour.weights)
+    _ck(ctx, ccall((:feast_set_contour, libfeast), Cint, (Ptr{Cvoid}, Cint, Ptr{ComplexF64}, Ptr{ComplexF64}), ctx.h, nodes, z, w))
+    _ck(ctx, ccall((:feast_set_solver, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cint, Cint), ctx.h, 2, 0, 1e-3, 4000, false))
+    _ck(ctx, ccall((:feast_set_subspace, libfeast), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{ComplexF64}, Int64), ctx.h, N, m₀, X, N))
+    _ck(ctx, ccall((:feast_orthonormalize_X, libfeast), Cint, (Ptr{Cvoid},), ctx.h))
+    Λ, res = zeros(ComplexF64, m₀), Array{Float64}(undef, m₀)
+    Rf, G1 = zeros(ComplexF64, m₀, m₀), zeros(ComplexF64, m₀, m₀)
+    for nit = 0:iter
+        nit == 1 && _ck(ctx, ccall((:feast_set_solver, libfeast), Cint, (Ptr{Cvoid}, Cint, Cint, Cdouble, Cint, Cint), ctx.h, 2, 0, 1e-8, 4000, false))
+        _ck(ctx, ccall((:feast_contour_apply, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Cint, Ptr{Cvoid}),
+                       ctx.h, Λ, nit == 0, C_NULL); allow=(0, 2000))
+        _ck(ctx, ccall((:feast_beyn_reduce, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}), ctx.h, Rf, G1))
+        S = svd!(copy(Rf)); F = eigen!((S.U' * G1) * S.V * Diagonal(1 ./ S.S))
+        Λ .= F.values
+        Xq = convert(Matrix{ComplexF64}, S.U * F.vectors)
+        _ck(ctx, ccall((:feast_recover_residual, libfeast), Cint, (Ptr{Cvoid}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{Cdouble}), ctx.h, Xq, Λ, res))
+        res_inside = res[in_contour.(Λ, c, r)]
+        if nit >= 1 && size(res_inside, 1) > 0 && maximum(res_inside) < ϵ                 # nlfeast.jl:164
             break
         end
     end
