@@ -191,6 +191,9 @@ def rr_phase(ctx, generalized=True):
     return Lam, res
 
 
+FIRST_PASS_TOL = 1e-3   # e2e leg: inner tolerance of the first contour pass (random start: the 16-node filter contracts by ~5e-5 per pass anyway)
+
+
 def e2e_solve(fs, A, B, contour, X0, solver_opts, device, hook):
     """The public call with HOST buffers, run to convergence (context creation, operator upload, layout build, all
     outer iterations and the download of X inside the timed region)."""
@@ -198,7 +201,8 @@ def e2e_solve(fs, A, B, contour, X0, solver_opts, device, hook):
     Xh = X0.copy(order="F")
     t0 = time.perf_counter()
     ctx = fs.FeastContext(device=device)
-    e, v, rs = fs.gen_feast(Xh, A, B, contour, eps=EPS, iter=10, ctx=ctx, solver_opts=solver_opts, stats=st, comm=hook)
+    e, v, rs = fs.gen_feast(Xh, A, B, contour, eps=EPS, iter=10, ctx=ctx, solver_opts=dict(solver_opts, first_pass_tol=FIRST_PASS_TOL),
+                            stats=st, comm=hook)
     ctx.close()
     return e, rs, st, time.perf_counter() - t0
 
@@ -376,6 +380,7 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "node_solves/s", "h2d_bytes_per_step": int(h2d / max(1, iters_with_solves)),
                 "d2h_bytes_per_step": int(d2h / max(1, iters_with_solves)), "time_to_solution_s": tts,
                 "api": "feastsolver_jl_b200.gen_feast(X, A, B, contour) with host numpy/scipy buffers, to convergence",
+                "inner_tol_schedule": [FIRST_PASS_TOL, INNER_TOL],
                 "phases_rank0_s": phases, "phases_max_over_ranks_s": phases_max,
                 "preconditioner_setup_s": st_e2e["preconditioner"]["setup_s"]},
         "gpu_launches": launches, "host_cpus": os.cpu_count(),

@@ -450,6 +450,13 @@ def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, 
                     comm_err.append(e)
             comm_thread = threading.Thread(target=_comm)
             comm_thread.start()
+        # inner-tolerance schedule (the reference's own precedent: 1e-3 in the first pass, tight afterwards, nlfeast.jl:106,139):
+        # the first contour pass starts from a random subspace and cannot gain more than the filter's contraction anyway
+        solver_opts = dict(solver_opts)
+        first_tol = solver_opts.pop("first_pass_tol", None)
+        later_tol = solver_opts.get("inner_tol", 1e-8)
+        if first_tol is not None:
+            solver_opts["inner_tol"] = max(float(first_tol), float(later_tol))
         ctx.set_solver(store=store, **solver_opts)   # before the operators: the device layout is then built once
         ctx.set_operator(0, A)
         if generalized:
@@ -490,6 +497,10 @@ def _linear_driver(X, A, B, contour, iter, eps, debug, store, ctx, solver_opts, 
             if nit < iter:  # feast.jl:57
                 st = ctx.contour_apply(Lam)
                 rec.update(st)
+                rec["inner_tol"] = solver_opts["inner_tol"]
+                if first_tol is not None and nit == 0:
+                    solver_opts["inner_tol"] = later_tol
+                    ctx.set_solver(store=store, **solver_opts)   # same solver kind: the device layout is kept
                 tick("contour_passes_s")
                 ph.setdefault("contour_pass_s", []).append(st["t_total_ms"] / 1e3)
                 ph.setdefault("contour_pass_allreduce_s", []).append(st["t_reduce_ms"] / 1e3)
