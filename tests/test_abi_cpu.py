@@ -284,3 +284,20 @@ def test_group_choice_of_the_column_sharded_loop(lib):
     assert lib.feast_debug_pick_groups(16, _lib.ptr(flat), 8, 64, _lib.ptr(own)) in (4, 8)   # balanced either way: widest slices win
     one = np.array([100.0] + [1.0] * 15)
     assert lib.feast_debug_pick_groups(16, _lib.ptr(one), 8, 64, _lib.ptr(own)) == 1           # one dominant node: split its columns
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm: oracle port on the host cores) on a tiny grid: one JSON line with the
+    contract keys, impl = reference, no GPU and no libfeast_cuda involved."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--grid", "10", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["metric"] == "contour_node_solves_per_sec" and d["unit"] == "node_solves/s"
+    assert d["steps"] == 2 and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
