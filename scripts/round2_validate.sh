@@ -1,5 +1,7 @@
 #!/bin/bash
-# First GPU call of round 2: validates everything written after the round-1 GPU budget was spent (all of it was opt-in).
+# First GPU call of round 2 (kept as a record; output: profiles/r2_round2_validate.log): validated everything written after the
+# round-1 GPU budget was spent.  The FEAST_BAND_PIVOT / FEAST_RUN_EXPERIMENTAL / FEAST_RUN_EXPENSIVE switches it sets no longer exist:
+# the pivoted band LU is the only banded path and the tests are part of the default GPU suite.
 #   gpurun --timeout 1500 -- 'bash scripts/round2_validate.sh > gpurun_out/round2_validate.log 2>&1; tail -40 gpurun_out/round2_validate.log'
 set -x
 nvidia-smi -L
